@@ -1,0 +1,11 @@
+"""Importable alias of the package directory `mixed-gemmul8_b200/` (its name is not a Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mixed-gemmul8_b200")
+_spec = importlib.util.spec_from_file_location("gemmul8_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,131 @@
+/*
+ * gemmul8_b200.h -- C ABI of the B200-native Ozaki-scheme-II GEMM emulation.
+ *
+ * This is the drop-in boundary for the hot path of ptrkgtsch/mixed-GEMMul8:
+ *   gemmul8::workSize  (reference GEMMul8/include/gemmul8.hpp:18-22, GEMMul8/src/gemmul8.cu:129-147)
+ *   gemmul8::gemm<..>  (reference GEMMul8/include/gemmul8.hpp:29-287, GEMMul8/src/gemmul8.cu:149-1316)
+ * Plain C types only: pointers, sizes and enums.  The C++ drop-in header include/gemmul8.hpp
+ * (namespace gemmul8, same template specialisations as the reference) is a thin inline shim over
+ * these entry points, and INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * All matrices are column-major device pointers exactly as in the reference; alpha/beta are HOST
+ * pointers to one element of C's type (reference dereferences them on the host,
+ * GEMMul8/src/gemmul8.cu:288).  `work` is a device buffer of at least gemmul8_b200_worksize()
+ * bytes, 16-byte aligned.  Every call is asynchronous on `stream` unless GEMMUL8_FLAG_TIMERS is set.
+ *
+ * There is no CPU fallback: every entry point that computes returns GEMMUL8_ERR_CUDA when no
+ * sm_100 device/context is available.
+ */
+#ifndef GEMMUL8_B200_H
+#define GEMMUL8_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of A, B, C (reference: the 12 template specialisations, gemmul8.hpp:49-287) */
+typedef enum {
+    GEMMUL8_F32 = 0, /* float            */
+    GEMMUL8_F64 = 1, /* double           */
+    GEMMUL8_C32 = 2, /* cuFloatComplex   */
+    GEMMUL8_C64 = 3  /* cuDoubleComplex  */
+} gemmul8_dtype_t;
+
+/* same numbering as gemmul8::computeType_t (gemmul8.hpp:7-12) */
+typedef enum {
+    GEMMUL8_REAL_DEFAULT              = 0,
+    GEMMUL8_COMPLEX_BIG_MATRIX_ENCODE = 1,
+    GEMMUL8_COMPLEX_CLASSIC_MULT      = 2,
+    GEMMUL8_COMPLEX_KARATSUBA_MULT    = 3
+} gemmul8_compute_t;
+
+/* same numbering as cublasOperation_t */
+typedef enum { GEMMUL8_OP_N = 0, GEMMUL8_OP_T = 1, GEMMUL8_OP_C = 2 } gemmul8_op_t;
+
+typedef enum {
+    GEMMUL8_OK              = 0,
+    GEMMUL8_ERR_COMPUTETYPE = 1, /* reference prints "Unsupported compute type..." and returns zeros */
+    GEMMUL8_ERR_ARGUMENT    = 2, /* num_moduli outside 2..20, k > 2^17, null pointers, bad dtype combo */
+    GEMMUL8_ERR_CUDA        = 3  /* CUDA runtime/driver error, or no sm_100 device */
+} gemmul8_status_t;
+
+enum {
+    GEMMUL8_FLAG_TIMERS = 1u, /* bracket the 4 phases with CUDA events and fill timers_ns (synchronises) */
+    GEMMUL8_FLAG_STAGE_SCALING  = 1u << 4, /* run only phase 0: shifts + residue slices (parity tests) */
+    GEMMUL8_FLAG_STAGE_RESIDUES = 1u << 5, /* run phases 0-2: ... + per-modulus products mod m_j      */
+    GEMMUL8_FLAG_GEMM_SIMT      = 1u << 8  /* debug: use the CUDA-core int8 GEMM instead of tcgen05   */
+};
+
+/* Arguments of one gemm call, in the reference's argument order (gemmul8.hpp:30-47). */
+typedef struct {
+    int op_A, op_B;            /* gemmul8_op_t */
+    size_t m, n, k;
+    const void *alpha;         /* host pointer, type of C */
+    const void *A; size_t lda; /* device */
+    const void *B; size_t ldb; /* device */
+    const void *beta;          /* host pointer, type of C */
+    void *C; size_t ldc;       /* device */
+    unsigned num_moduli;       /* 2..20 */
+    int fastmode;              /* 1 = fast (vector-norm bound), 0 = accurate (int8 bound product) */
+    void *work;                /* device, >= gemmul8_b200_worksize bytes */
+    int compute_type;          /* gemmul8_compute_t */
+    int dtype_A, dtype_B, dtype_C; /* gemmul8_dtype_t */
+    void *stream;              /* cudaStream_t (NULL = legacy default stream, as the reference) */
+    unsigned flags;
+    double timers_ns[4];       /* out: {scaling, int8 GEMM, int32->residue, inverse scaling} in ns
+                                  (reference returns the same 4 numbers, gemmul8.cu:17,291).  The
+                                  residue reduction is fused into the GEMM epilogue here, so [2] = 0. */
+} gemmul8_b200_args;
+
+/* Byte offsets of the sub-buffers inside `work`; identical to the reference's carve
+ * (GEMMul8/src/gemmul8.cu:229-234, :659-664, :806-815) so that tests can compare them bit-for-bit. */
+typedef struct {
+    size_t lda8i;   /* = ldb8i: padded inner dimension (multiple of 16)              */
+    size_t m_pad;   /* padded row count of the product (multiple of 4)               */
+    size_t sizeA;   /* elements per modulus slice of A   (lda8i * m_pad)             */
+    size_t sizeB;   /* elements per modulus slice of B   (lda8i * n)                 */
+    size_t sizeC;   /* elements per modulus residue matrix (multiple of 16)          */
+    size_t off_A8i, off_A8i_imag;   /* int8  [N][sizeA]  (imag: CLASSIC/KARATSUBA only) */
+    size_t off_B8i, off_B8i_imag;   /* int8  [N][sizeB]                               */
+    size_t off_C8u, off_C8u_imag;   /* uint8 [N][sizeC]                               */
+    size_t off_C32i, off_C32i_imag; /* int32 [sizeC] scratch (accurate-mode bound product) */
+    size_t off_sftA, off_sftB;      /* int16 shifts (stored negated, as the reference) */
+    size_t total;                   /* == gemmul8_b200_worksize()                     */
+} gemmul8_b200_layout;
+
+/* reference: gemmul8::workSize, GEMMul8/src/gemmul8.cu:129-147.  Returns 0 (and prints
+ * "Unknown compute type") for an invalid compute_type, as the reference does. */
+size_t gemmul8_b200_worksize(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type);
+
+/* The carve of `work`; returns GEMMUL8_ERR_COMPUTETYPE for an invalid compute_type. */
+int gemmul8_b200_work_layout(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type,
+                             gemmul8_b200_layout *out);
+
+/* reference: gemmul8::gemm<TA,TB,TC>, GEMMul8/src/gemmul8.cu:149-1316. */
+int gemmul8_b200_gemm(gemmul8_b200_args *args);
+
+/* Same call with HOST matrices: copies op inputs host->device (and C when beta != 0), runs the
+ * emulation and copies C back.  `dev_scratch` must hold A, B, C and the workspace
+ * (gemmul8_b200_host_scratch_size bytes).  This is the end-to-end plugin call timed by bench.py. */
+size_t gemmul8_b200_host_scratch_size(const gemmul8_b200_args *args);
+int gemmul8_b200_gemm_host(gemmul8_b200_args *args_with_host_matrices, void *dev_scratch);
+
+/* Debug/parity: raw int32 product of modulus slice `j` (what the reference's cublasGemmEx at
+ * gemmul8.cu:265 writes into C32i), column-major with leading dimension m_pad.  Requires the
+ * slices to be present in `work` (GEMMUL8_FLAG_STAGE_SCALING or a full gemm call). */
+int gemmul8_b200_product_i32(const gemmul8_b200_args *args, unsigned j, int32_t *C32i_out, int imag_part);
+
+/* Constant tables (moduli, CRT weights, ...) for host-side tooling; row = num_moduli - 2. */
+int gemmul8_b200_modulus(unsigned j);                /* m_j, j in 0..19 */
+double gemmul8_b200_crt_weight(unsigned num_moduli, unsigned j, int part /*0=single,1=hi,2=lo*/);
+
+const char *gemmul8_b200_last_error(void);
+const char *gemmul8_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMMUL8_B200_H */

@@ -1,0 +1,57 @@
+"""Build the in-tree shared libraries with nvcc for sm_100a (cross-compiles without a GPU).
+
+  libgemmul8_b200.so        product: C ABI (include/gemmul8_b200.h), kernels, no cuBLAS dependency
+  libgemmul8_b200_aux.so    measurement helpers used by tests / bench only (phi-matrix generator,
+                            double-double truth GEMM, cuBLAS native baselines)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libgemmul8_b200.so")
+AUX = os.path.join(HERE, "libgemmul8_b200_aux.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found")
+    return exe
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def build(force=False, verbose=False):
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gemmul8_b200.h")]
+    core = [os.path.join(CSRC, f) for f in ("oz_api.cu", "oz_scale.cu", "oz_gemm.cu", "oz_crt.cu", "oz_complex.cu")
+            if os.path.exists(os.path.join(CSRC, f))]
+    out = ""
+    if force or _stale(LIB, deps):
+        extra = ["-Xptxas", "-v"] if verbose else []
+        out += _run([nvcc(), *ARCH, *COMMON, *extra, "-shared", "-o", LIB, *core])
+    aux_src = os.path.join(CSRC, "oz_aux.cu")
+    if os.path.exists(aux_src) and (force or _stale(AUX, [aux_src])):
+        out += _run([nvcc(), *ARCH, *COMMON, "-shared", "-o", AUX, aux_src, "-lcublas"])
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,290 @@
+// C ABI + host orchestration of the B200-native Ozaki-II GEMM emulation (see include/gemmul8_b200.h).
+//
+// Differences from the reference's host path (GEMMul8/src/gemmul8.cu:149-577), all deliberate:
+//   * no cudaDeviceSynchronize between phases (reference: 2 + 4N per call, gemmul8.cu:10-18) and no
+//     per-call cudaMemcpyToSymbol (gemmul8.cu:236-241): tables are static __constant__ data;
+//   * everything is enqueued on the caller's stream; the call is thread-safe (no mutable globals);
+//   * the N int8 GEMMs + N int32->uint8 passes are ONE persistent tcgen05 kernel (oz_gemm.cu);
+//   * the accurate-mode bound product never materialises C32i: its epilogue reduces row / column
+//     maxima directly into two small int32 vectors.
+// The carve of `work` is kept identical to the reference (gemmul8.cu:229-234) so that parity tests
+// can compare the int8 slices, the shift vectors and the uint8 residues in place.
+#include "../../include/gemmul8_b200.h"
+#include "oz_common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *where) {
+    return fail(GEMMUL8_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+inline size_t ceil_to(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool is_complex(int dt) { return dt == GEMMUL8_C32 || dt == GEMMUL8_C64; }
+size_t elem_size(int dt) { return dt == GEMMUL8_F32 ? 4 : dt == GEMMUL8_F64 ? 8 : dt == GEMMUL8_C32 ? 8 : 16; }
+
+// reference: workSize_real / workSize_bigmatrix / workSize_kara, GEMMul8/src/gemmul8.cu:27-127
+bool compute_layout(size_t m, size_t n, size_t k, unsigned N, int ct, oz::Layout &L) {
+    const bool big = ct == GEMMUL8_COMPLEX_BIG_MATRIX_ENCODE;
+    const bool kara = ct == GEMMUL8_COMPLEX_CLASSIC_MULT || ct == GEMMUL8_COMPLEX_KARATSUBA_MULT;
+    if (!(ct == GEMMUL8_REAL_DEFAULT || big || kara)) return false;
+    L.lda8i = ceil_to(big ? 2 * k : k, 16);
+    L.m_pad = ceil_to(big ? 2 * m : m, 4);
+    L.sizeA = L.lda8i * L.m_pad;
+    L.sizeB = L.lda8i * n;
+    L.sizeC = ceil_to(L.m_pad * n, 16);
+    const size_t vecA = ceil_to(m, 16), vecB = ceil_to(n, 16);
+    size_t off = 0;
+    L.off_A8i = off;       off += L.sizeA * N;
+    L.off_A8i_imag = off;  if (kara) off += L.sizeA * N;
+    L.off_B8i = off;       off += L.sizeB * N;
+    L.off_B8i_imag = off;  if (kara) off += L.sizeB * N;
+    L.off_C8u = off;       off += L.sizeC * N;
+    L.off_C8u_imag = off;  if (kara) off += L.sizeC * N;
+    L.off_C32i = off;      off += 4 * L.sizeC;
+    L.off_C32i_imag = off; if (kara) off += 4 * L.sizeC;
+    L.off_sftA = off;      off += 2 * vecA;
+    L.off_sftB = off;      off += 2 * vecB;
+    L.total = off;
+    return true;
+}
+
+int check_args(const gemmul8_b200_args *a) {
+    if (!a) return fail(GEMMUL8_ERR_ARGUMENT, "null argument block");
+    if (a->num_moduli < 2 || a->num_moduli > 20) return fail(GEMMUL8_ERR_ARGUMENT, "num_moduli must be in 2..20");
+    if (a->k > (size_t(1) << 17)) return fail(GEMMUL8_ERR_ARGUMENT, "k must be <= 2^17");
+    if (a->m > (size_t(1) << 24) || a->n > (size_t(1) << 18)) return fail(GEMMUL8_ERR_ARGUMENT, "m or n too large");
+    if (a->dtype_A < 0 || a->dtype_A > 3 || a->dtype_B < 0 || a->dtype_B > 3 || a->dtype_C < 0 || a->dtype_C > 3)
+        return fail(GEMMUL8_ERR_ARGUMENT, "bad dtype tag");
+    const bool cplx = is_complex(a->dtype_C);
+    if (is_complex(a->dtype_A) != cplx || is_complex(a->dtype_B) != cplx)
+        return fail(GEMMUL8_ERR_ARGUMENT, "A, B and C must be all real or all complex");
+    // reference: real types accept only REAL_DEFAULT, complex types only the COMPLEX_* values
+    // (GEMMul8/src/gemmul8.cu:174-177, :1166-1177): message on stderr, zero timers, C untouched
+    const bool ct_ok = cplx ? (a->compute_type >= 1 && a->compute_type <= 3) : (a->compute_type == GEMMUL8_REAL_DEFAULT);
+    if (!ct_ok) {
+        fprintf(stderr, "Unsupported compute type for the argument types.\n");
+        return fail(GEMMUL8_ERR_COMPUTETYPE, "unsupported compute type for the argument types");
+    }
+    if (a->m && a->n && (!a->C || !a->work || !a->alpha || !a->beta)) return fail(GEMMUL8_ERR_ARGUMENT, "null pointer");
+    if (a->m && a->n && a->k && (!a->A || !a->B)) return fail(GEMMUL8_ERR_ARGUMENT, "null matrix pointer");
+    return GEMMUL8_OK;
+}
+
+struct PhaseTimer {
+    bool on; cudaStream_t st; cudaEvent_t ev[5]; int n = 0;
+    PhaseTimer(bool enable, cudaStream_t s) : on(enable), st(s) {
+        if (on) for (auto &e : ev) cudaEventCreate(&e);
+    }
+    void mark() { if (on) cudaEventRecord(ev[n++], st); }
+    void finish(double *out_ns) {
+        if (!on) return;
+        cudaEventSynchronize(ev[n - 1]);
+        // marks: 0 start, 1 after scaling, 2 after gemm(+residues), 3 after crt
+        float ms;
+        const int slot[3] = {0, 1, 3};
+        for (int i = 0; i + 1 < n && i < 3; ++i) {
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            out_ns[slot[i]] = (double)ms * 1e6;
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+};
+
+#define OZ_CUDA(call, where)                                   \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return fail_cuda(e__, where);  \
+    } while (0)
+
+// shifts + residue slices of one real operand.  `rows_are_vectors`: the vectors that get a common
+// shift are rows of the stored column-major matrix (op_A == N for A, op_B != N for B).
+int scale_operand(int dtype, bool strided, const void *X, size_t ld, size_t nvec, size_t len, int ref_width,
+                  float log2M_fast, unsigned N, int8_t *slices, size_t ld8i, size_t inc, int16_t *sft, bool fast,
+                  cudaStream_t st) {
+    if (fast) OZ_CUDA(oz::launch_fast_shifts(dtype, strided, X, ld, nvec, len, ref_width, log2M_fast, sft, st), "fast shifts");
+    OZ_CUDA(oz::launch_encode(dtype, strided, X, ld, nvec, len, sft, N, slices, ld8i, inc, st), "encode");
+    return GEMMUL8_OK;
+}
+
+int gemm_real(gemmul8_b200_args *a) {
+    const size_t m = a->m, n = a->n, k = a->k;
+    const unsigned N = a->num_moduli, ti = N - 2;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    oz::Layout L;
+    compute_layout(m, n, k, N, GEMMUL8_REAL_DEFAULT, L);
+    uint8_t *work = static_cast<uint8_t *>(a->work);
+    int8_t *A8i   = reinterpret_cast<int8_t *>(work + L.off_A8i);
+    int8_t *B8i   = reinterpret_cast<int8_t *>(work + L.off_B8i);
+    uint8_t *C8u  = work + L.off_C8u;
+    int16_t *sftA = reinterpret_cast<int16_t *>(work + L.off_sftA);
+    int16_t *sftB = reinterpret_cast<int16_t *>(work + L.off_sftB);
+
+    const bool a_strided = a->op_A == GEMMUL8_OP_N;  // rows of column-major A
+    const bool b_strided = a->op_B != GEMMUL8_OP_N;  // rows of column-major B
+    const int ref_width  = oz::ref_reduce_width(a->dtype_A, a->dtype_B, a->dtype_C);
+    const bool simt      = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) != 0;
+    auto gemm = simt ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
+
+    PhaseTimer timer((a->flags & GEMMUL8_FLAG_TIMERS) != 0, st);
+    timer.mark();
+
+    // ---------------- phase 0: scaling ----------------
+    if (a->fastmode) {
+        const float l2 = oz::host_tab::OZ_LOG2M_FAST[ti];
+        int rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, l2, N, A8i, L.lda8i, L.sizeA, sftA, true, st);
+        if (rc) return rc;
+        rc = scale_operand(a->dtype_B, b_strided, a->B, a->ldb, n, k, ref_width, l2, N, B8i, L.lda8i, L.sizeB, sftB, true, st);
+        if (rc) return rc;
+    } else {
+        // reference: int8tc::scaling, GEMMul8/src/scaling.hpp:3053-3136
+        OZ_CUDA(oz::launch_bound_extract(a->dtype_A, a_strided, a->A, a->lda, m, k, A8i, L.lda8i, sftA, st), "bound extract A");
+        OZ_CUDA(oz::launch_bound_extract(a->dtype_B, b_strided, a->B, a->ldb, n, k, B8i, L.lda8i, sftB, st), "bound extract B");
+        // The bound product only needs its row / column maxima.  They live in the (still unused)
+        // second modulus slice of A8i / B8i: 4*m_pad <= lda8i*m_pad and 4*n <= lda8i*n always hold.
+        int32_t *rowmax = reinterpret_cast<int32_t *>(A8i + L.sizeA);
+        int32_t *colmax = reinterpret_cast<int32_t *>(B8i + L.sizeB);
+        OZ_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(int32_t) * m, st), "memset row maxima");
+        OZ_CUDA(cudaMemsetAsync(colmax, 0, sizeof(int32_t) * n, st), "memset col maxima");
+        oz::GemmProblem bp{};
+        bp.A8i = A8i; bp.B8i = B8i; bp.rowsA = m; bp.rowsB = n; bp.ld8i = L.lda8i; bp.sizeA = L.sizeA; bp.sizeB = L.sizeB;
+        bp.num_slices = 1; bp.first_modulus = 0; bp.rowmax = rowmax; bp.colmax = colmax;
+        OZ_CUDA(gemm(bp, oz::EPI_ABSMAX, st), "bound product");
+        const float l2 = oz::host_tab::OZ_LOG2M_ACC[ti];
+        OZ_CUDA(oz::launch_accurate_shifts(m, rowmax, l2, sftA, st), "accurate shifts A");
+        OZ_CUDA(oz::launch_accurate_shifts(n, colmax, l2, sftB, st), "accurate shifts B");
+        int rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, 0.f, N, A8i, L.lda8i, L.sizeA, sftA, false, st);
+        if (rc) return rc;
+        rc = scale_operand(a->dtype_B, b_strided, a->B, a->ldb, n, k, ref_width, 0.f, N, B8i, L.lda8i, L.sizeB, sftB, false, st);
+        if (rc) return rc;
+    }
+    timer.mark();
+    if (a->flags & GEMMUL8_FLAG_STAGE_SCALING) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
+
+    // ---------------- phases 1+2: all-moduli int8 GEMM with fused residue reduction ----------------
+    oz::GemmProblem gp{};
+    gp.A8i = A8i; gp.B8i = B8i; gp.rowsA = m; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
+    gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    OZ_CUDA(gemm(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+    timer.mark();
+    if (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
+
+    // ---------------- phase 3: CRT + inverse scaling ----------------
+    const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;  // numM == 2 (N >= 8) and fp64 out
+    OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, n, C8u, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, st), "crt");
+    timer.mark();
+    timer.finish(a->timers_ns);
+    return GEMMUL8_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gemmul8_b200_worksize(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type) {
+    oz::Layout L;
+    if (!compute_layout(m, n, k, num_moduli, compute_type, L)) {
+        fprintf(stderr, "Unknown compute type\n");  // reference: gemmul8.cu:142-145
+        return 0;
+    }
+    return L.total;
+}
+
+int gemmul8_b200_work_layout(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type, gemmul8_b200_layout *out) {
+    oz::Layout L;
+    if (!out) return fail(GEMMUL8_ERR_ARGUMENT, "null layout");
+    if (!compute_layout(m, n, k, num_moduli, compute_type, L)) return fail(GEMMUL8_ERR_COMPUTETYPE, "unknown compute type");
+    static_assert(sizeof(gemmul8_b200_layout) == sizeof(oz::Layout), "layout structs must match");
+    memcpy(out, &L, sizeof(L));
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_gemm(gemmul8_b200_args *a) {
+    if (a) for (double &t : a->timers_ns) t = 0.0;
+    int rc = check_args(a);
+    if (rc) return rc;
+    if (a->m == 0 || a->n == 0) return GEMMUL8_OK;
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+        return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (is_complex(a->dtype_C)) return fail(GEMMUL8_ERR_ARGUMENT, "complex types: not implemented yet in this build");
+    return gemm_real(a);
+}
+
+size_t gemmul8_b200_host_scratch_size(const gemmul8_b200_args *a) {
+    if (!a) return 0;
+    const size_t colsA = a->op_A == GEMMUL8_OP_N ? a->k : a->m, colsB = a->op_B == GEMMUL8_OP_N ? a->n : a->k;
+    size_t s = ceil_to(a->lda * colsA * elem_size(a->dtype_A), 256) + ceil_to(a->ldb * colsB * elem_size(a->dtype_B), 256) +
+               ceil_to(a->ldc * a->n * elem_size(a->dtype_C), 256);
+    return s + gemmul8_b200_worksize(a->m, a->n, a->k, a->num_moduli, a->compute_type);
+}
+
+int gemmul8_b200_gemm_host(gemmul8_b200_args *h, void *dev_scratch) {
+    int rc = check_args(h);
+    if (rc) return rc;
+    if (!dev_scratch) return fail(GEMMUL8_ERR_ARGUMENT, "null scratch");
+    cudaStream_t st = static_cast<cudaStream_t>(h->stream);
+    const size_t colsA = h->op_A == GEMMUL8_OP_N ? h->k : h->m, colsB = h->op_B == GEMMUL8_OP_N ? h->n : h->k;
+    const size_t bytesA = h->lda * colsA * elem_size(h->dtype_A), bytesB = h->ldb * colsB * elem_size(h->dtype_B);
+    const size_t bytesC = h->ldc * h->n * elem_size(h->dtype_C);
+    uint8_t *p = static_cast<uint8_t *>(dev_scratch);
+    void *dA = p; p += ceil_to(bytesA, 256);
+    void *dB = p; p += ceil_to(bytesB, 256);
+    void *dC = p; p += ceil_to(bytesC, 256);
+    gemmul8_b200_args d = *h;
+    d.A = dA; d.B = dB; d.C = dC; d.work = p;
+    OZ_CUDA(cudaMemcpyAsync(dA, h->A, bytesA, cudaMemcpyHostToDevice, st), "H2D A");
+    OZ_CUDA(cudaMemcpyAsync(dB, h->B, bytesB, cudaMemcpyHostToDevice, st), "H2D B");
+    bool beta_zero = true;
+    const size_t es = elem_size(h->dtype_C);
+    for (size_t i = 0; i < es; ++i) beta_zero &= static_cast<const unsigned char *>(h->beta)[i] == 0;
+    if (!beta_zero) OZ_CUDA(cudaMemcpyAsync(dC, h->C, bytesC, cudaMemcpyHostToDevice, st), "H2D C");
+    rc = gemmul8_b200_gemm(&d);
+    memcpy(h->timers_ns, d.timers_ns, sizeof(d.timers_ns));
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpyAsync(h->C, dC, bytesC, cudaMemcpyDeviceToHost, st), "D2H C");
+    OZ_CUDA(cudaStreamSynchronize(st), "sync");
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_product_i32(const gemmul8_b200_args *a, unsigned j, int32_t *C32i_out, int imag_part) {
+    int rc = check_args(a);
+    if (rc) return rc;
+    if (j >= a->num_moduli || !C32i_out || imag_part) return fail(GEMMUL8_ERR_ARGUMENT, "bad slice index / output");
+    oz::Layout L;
+    compute_layout(a->m, a->n, a->k, a->num_moduli, a->compute_type, L);
+    uint8_t *work = static_cast<uint8_t *>(a->work);
+    oz::GemmProblem gp{};
+    gp.A8i = reinterpret_cast<int8_t *>(work + L.off_A8i) + (size_t)j * L.sizeA;
+    gp.B8i = reinterpret_cast<int8_t *>(work + L.off_B8i) + (size_t)j * L.sizeB;
+    gp.rowsA = a->compute_type == GEMMUL8_COMPLEX_BIG_MATRIX_ENCODE ? 2 * a->m : a->m;
+    gp.rowsB = a->n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = 1; gp.first_modulus = j;
+    gp.C32i = C32i_out; gp.ldc32i = L.m_pad;
+    auto gemm = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
+    OZ_CUDA(gemm(gp, oz::EPI_INT32, static_cast<cudaStream_t>(a->stream)), "int32 product");
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_modulus(unsigned j) { return j < 20 ? oz::host_tab::OZ_MOD[j] : 0; }
+
+double gemmul8_b200_crt_weight(unsigned N, unsigned j, int part) {
+    if (N < 2 || N > 20 || j >= N) return 0.0;
+    if (part == 0) return oz::host_tab::OZ_W1[N - 2][j];
+    if (N < 8) return 0.0;
+    return part == 1 ? oz::host_tab::OZ_W2_HI[N - 8][j] : oz::host_tab::OZ_W2_LO[N - 8][j];
+}
+
+const char *gemmul8_b200_last_error(void) { return g_last_error.c_str(); }
+const char *gemmul8_b200_version(void) { return "gemmul8_b200 0.1 (sm_100a, tcgen05 kind::i8)"; }
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// All-moduli int8 x int8 -> int32 GEMM for sm_100a with the mod-m_j reduction fused into the epilogue.
+//
+// Replaces, for every modulus j, the reference's pair
+//     cublasGemmEx(OP_T, OP_N, m_pad, n, lda8i, A8i + j*sizeA, B8i + j*sizeB -> C32i)   GEMMul8/src/gemmul8.cu:265
+//     conv_32i_2_8u(j, sizeC, C32i, C8u + j*sizeC)                                      GEMMul8/src/conv_32i_2_8u.hpp:7-71
+// by ONE persistent kernel: the int32 product lives only in tensor memory; HBM sees the int8 slices
+// coming in (TMA, 128-byte swizzle) and one uint8 residue per element and modulus going out.
+//
+// Kernel anatomy (one CTA per SM, 256 threads):
+//   warp 0      TMA producer: 4-stage ring of {A tile 128 x 128 B, B tile 256 x 128 B}
+//   warp 1      MMA issuer  : tcgen05.mma.cta_group::1.kind::i8, M=128, N=256, K=32 per instruction,
+//                             accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue    : tcgen05.ld (lane == row), Barrett reduction mod m_j, byte stores
+// A work item is (C tile, modulus); items are ordered (band of 16 row-tiles, modulus, column tile,
+// row tile) so that the ~148 items in flight share one modulus and a compact block of A / B panels.
+//
+// Both operands are K-major exactly as the reference lays them out (A8i[j][row][k], B8i[j][col][k],
+// row stride lda8i), so a 3-D tensor map (k, row, modulus) serves all moduli and K / row tails are
+// zero-filled by TMA.
+#include "oz_common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace oz {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 128;  // int8 elements == bytes == one 128B swizzle atom
+constexpr int UMMA_K  = 32;
+constexpr int STAGES  = 4;
+constexpr int SMEM_A  = BLOCK_M * BLOCK_K;
+constexpr int SMEM_B  = BLOCK_N * BLOCK_K;
+constexpr int SMEM_STAGE = SMEM_A + SMEM_B;
+constexpr int SMEM_BARRIERS = 256;
+constexpr int SMEM_TOTAL = STAGES * SMEM_STAGE + SMEM_BARRIERS + 1024;  // + slack for 1024-B alignment
+constexpr int BAND_M = 16;  // row tiles per scheduling band
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, s8 x s8 -> s32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups (1024 B) are the
+// stride dimension; descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)0 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+    d |= (uint64_t)1 << 46;                         // version
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = s32, A = B = s8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t make_idesc(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Sched {
+    uint32_t tiles_m, tiles_n, slices, full_bands, per_band_full, total;
+    __host__ __device__ void init(uint32_t tm, uint32_t tn, uint32_t s) {
+        tiles_m = tm; tiles_n = tn; slices = s;
+        full_bands = tm / BAND_M;
+        per_band_full = BAND_M * tn * s;
+        total = tm * tn * s;
+    }
+    __device__ __forceinline__ void decode(uint32_t item, uint32_t &tm, uint32_t &tn, uint32_t &j) const {
+        uint32_t band = item / per_band_full, rem, bm;
+        if (band < full_bands) { rem = item - band * per_band_full; bm = BAND_M; }
+        else { band = full_bands; rem = item - full_bands * per_band_full; bm = tiles_m - full_bands * BAND_M; }
+        const uint32_t per_j = bm * tiles_n;
+        j = rem / per_j;
+        const uint32_t r2 = rem - j * per_j;
+        tn = r2 / bm;
+        tm = band * BAND_M + (r2 - tn * bm);
+    }
+};
+
+struct KernelArgs {
+    uint32_t rowsA, rowsB, num_kb, first_modulus;
+    Sched sched;
+    uint8_t *C8u; size_t ldc8u, sizeC;
+    int32_t *C32i; size_t ldc32i;
+    int32_t *rowmax; int32_t *colmax;
+};
+
+// canonical residue in [0, m) of a (possibly wrapped) int32; modulus index 0 is 256
+__device__ __forceinline__ uint32_t reduce_mod(int32_t x, int32_t m, int32_t inv) {
+    int32_t r = x - __mulhi(x, inv) * m;  // r in [-m, 2m)
+    r -= (r >= m) ? m : 0;
+    r += (r < 0) ? m : 0;
+    return (uint32_t)r;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const KernelArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base  = smem_base + STAGES * SMEM_STAGE;
+    // barrier slots (8 bytes each)
+    auto full_bar  = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const uint32_t total = args.sched.total;
+    const uint32_t num_kb = args.num_kb;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+                uint32_t tm, tn, j;
+                args.sched.decode(item, tm, tn, j);
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * SMEM_STAGE;
+                    mbar_expect_tx(full_bar(stage), SMEM_STAGE);
+                    tma_load_3d(sa, &map_a, full_bar(stage), (int)(kb * BLOCK_K), (int)(tm * BLOCK_M), (int)j);
+                    tma_load_3d(sa + SMEM_A, &map_b, full_bar(stage), (int)(kb * BLOCK_K), (int)(tn * BLOCK_N), (int)j);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * SMEM_STAGE;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + SMEM_A);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | (uint32_t)k) != 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(tfull_bar(acc));  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+            uint32_t tm, tn, j;
+            args.sched.decode(item, tm, tn, j);
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+
+            const uint32_t row  = tm * BLOCK_M + q * 32 + lane;
+            const uint32_t col0 = tn * BLOCK_N;
+            const bool row_ok   = row < args.rowsA;
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+
+            if constexpr (EPI == EPI_RESIDUE) {
+                const uint32_t mj  = args.first_modulus + j;
+                const int32_t m    = dev_tab::OZ_MOD[mj];
+                const int32_t inv  = (int32_t)(4294967296ull / (uint32_t)m);
+                uint8_t *__restrict__ out = args.C8u + (size_t)j * args.sizeC + row;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const uint32_t col = col0 + c + e;
+                            if (col < args.rowsB) {
+                                const uint32_t r = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
+                                out[(size_t)col * args.ldc8u] = (uint8_t)r;
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (EPI == EPI_INT32) {
+                int32_t *__restrict__ out = args.C32i + row;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const uint32_t col = col0 + c + e;
+                            if (col < args.rowsB) out[(size_t)col * args.ldc32i] = (int32_t)v[e];
+                        }
+                    }
+                }
+            } else {  // EPI_ABSMAX
+                int32_t rmax = 0;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t col = col0 + c + e;
+                        int32_t a = (row_ok && col < args.rowsB) ? abs((int32_t)v[e]) : 0;
+                        rmax = max(rmax, a);
+                        a = max(a, __shfl_xor_sync(0xffffffffu, a, 16));
+                        a = max(a, __shfl_xor_sync(0xffffffffu, a, 8));
+                        a = max(a, __shfl_xor_sync(0xffffffffu, a, 4));
+                        a = max(a, __shfl_xor_sync(0xffffffffu, a, 2));
+                        a = max(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                        if (lane == 0 && col < args.rowsB && a > 0) atomicMax(args.colmax + col, a);
+                    }
+                }
+                if (row_ok && rmax > 0) atomicMax(args.rowmax + row, rmax);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core cross-check (debug flag GEMMUL8_FLAG_GEMM_SIMT): one thread per C element, dp4a.
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void oz_gemm_simt_kernel(const int8_t *__restrict__ A8i, const int8_t *__restrict__ B8i, size_t sizeA,
+                                    size_t sizeB, size_t ld8i, KernelArgs args) {
+    const uint32_t row = blockIdx.x * 32 + threadIdx.x;
+    const uint32_t col = blockIdx.y * 8 + threadIdx.y;
+    const uint32_t j   = blockIdx.z;
+    if (row >= args.rowsA || col >= args.rowsB) return;
+    const int *a = reinterpret_cast<const int *>(A8i + (size_t)j * sizeA + (size_t)row * ld8i);
+    const int *b = reinterpret_cast<const int *>(B8i + (size_t)j * sizeB + (size_t)col * ld8i);
+    int acc = 0;
+    for (size_t k = 0; k < ld8i / 4; ++k) acc = __dp4a(a[k], b[k], acc);
+    if constexpr (EPI == EPI_RESIDUE) {
+        const uint32_t mj = args.first_modulus + j;
+        const int32_t m   = dev_tab::OZ_MOD[mj];
+        const int32_t inv = (int32_t)(4294967296ull / (uint32_t)m);
+        args.C8u[(size_t)j * args.sizeC + (size_t)col * args.ldc8u + row] =
+            (uint8_t)((mj == 0) ? ((uint32_t)acc & 0xffu) : reduce_mod(acc, m, inv));
+    } else if constexpr (EPI == EPI_INT32) {
+        args.C32i[(size_t)col * args.ldc32i + row] = acc;
+    } else {
+        const int a_ = abs(acc);
+        if (a_ > 0) { atomicMax(args.rowmax + row, a_); atomicMax(args.colmax + col, a_); }
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// (k, row, slice) view of a stack of K-major int8 slices; box = 128 bytes of k x box_rows rows
+bool make_operand_map(CUtensorMap *map, const int8_t *base, size_t ld8i, size_t rows, size_t slices, size_t slice_stride,
+                      uint32_t box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3]    = {(cuuint64_t)ld8i, (cuuint64_t)rows, (cuuint64_t)slices};
+    cuuint64_t strides[2] = {(cuuint64_t)ld8i, (cuuint64_t)slice_stride};
+    cuuint32_t box[3]     = {(cuuint32_t)BLOCK_K, box_rows, 1};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+KernelArgs make_args(const GemmProblem &p) {
+    KernelArgs a{};
+    a.rowsA = (uint32_t)p.rowsA; a.rowsB = (uint32_t)p.rowsB;
+    a.num_kb = (uint32_t)((p.ld8i + BLOCK_K - 1) / BLOCK_K);
+    a.first_modulus = p.first_modulus;
+    a.sched.init((uint32_t)((p.rowsA + BLOCK_M - 1) / BLOCK_M), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N), p.num_slices);
+    a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
+    a.C32i = p.C32i; a.ldc32i = p.ldc32i;
+    a.rowmax = p.rowmax; a.colmax = p.colmax;
+    return a;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int EPI>
+cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, BLOCK_M)) return cudaErrorInvalidValue;
+    if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, BLOCK_N)) return cudaErrorInvalidValue;
+    KernelArgs a = make_args(p);
+    auto kern = oz_gemm_tcgen05_kernel<EPI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
+    kern<<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(ma, mb, a);
+    return cudaGetLastError();
+}
+
+template <int EPI>
+cudaError_t launch_simt_t(const GemmProblem &p, cudaStream_t st) {
+    KernelArgs a = make_args(p);
+    dim3 block(32, 8), grid((unsigned)((p.rowsA + 31) / 32), (unsigned)((p.rowsB + 7) / 8), p.num_slices);
+    oz_gemm_simt_kernel<EPI><<<grid, block, 0, st>>>(p.A8i, p.B8i, p.sizeA, p.sizeB, p.ld8i, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStream_t st) {
+    if (p.rowsA == 0 || p.rowsB == 0 || p.num_slices == 0) return cudaSuccess;
+    switch (epi) {
+        case EPI_RESIDUE: return launch_tc<EPI_RESIDUE>(p, st);
+        case EPI_INT32:   return launch_tc<EPI_INT32>(p, st);
+        case EPI_ABSMAX:  return launch_tc<EPI_ABSMAX>(p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemm_simt(const GemmProblem &p, GemmEpilogue epi, cudaStream_t st) {
+    if (p.rowsA == 0 || p.rowsB == 0 || p.num_slices == 0) return cudaSuccess;
+    switch (epi) {
+        case EPI_RESIDUE: return launch_simt_t<EPI_RESIDUE>(p, st);
+        case EPI_INT32:   return launch_simt_t<EPI_INT32>(p, st);
+        case EPI_ABSMAX:  return launch_simt_t<EPI_ABSMAX>(p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace oz

@@ -1,0 +1,500 @@
+// Scaling phase of the Ozaki-II emulation on B200: shift (power-of-two scale) selection per row of
+// op(A) / column of op(B), and residue encoding of the scaled integers into int8 slices.
+//
+// What is computed follows the reference exactly (results are bit-identical):
+//   fast-mode shift      GEMMul8/src/scaling.hpp:155-213 (reduction), :3373-3383 (compute_sft)
+//   accurate-mode bound  GEMMul8/src/scaling.hpp:1897-1941, :2215-2260 (extract), :1504-1506 (compute_sft)
+//   residue encode       GEMMul8/src/scaling.hpp:215-230 (mod_8i), :693-751, :1091-1148
+// How it is computed is different: the reference runs one CTA per vector and gathers strided
+// operands element by element; here strided operands are processed 32 vectors at a time with
+// lane == vector (every warp load is one contiguous 256-byte segment), the encoder transposes
+// through shared memory and emits 16-byte stores along K, and shifts / encode are separate kernels
+// so the accurate mode reuses the encoder.
+//
+// Bit-exactness note.  The fast-mode bound uses a sum of squares accumulated with round-up FMAs,
+// so its bits depend on the association order of the reference's reduction: thread t of a W-wide
+// CTA (W = 128, or 512 for gemm<float>) accumulates elements t, t+W, t+2W, ... in order, warps are
+// combined with a shfl_down tree and -- a quirk of the reference -- the per-warp value that is kept
+// is the one that ends up in lane 1 (scaling.hpp:190-195), which omits lane 0's partial and counts
+// lane 16's twice.  We reproduce that order with W "virtual threads" per vector.
+#include "oz_common.cuh"
+
+namespace oz {
+namespace {
+
+using dev_tab::OZ_MOD;
+using dev_tab::OZ_RCP32;
+using dev_tab::OZ_RCP64;
+
+template <typename T> struct Real { using type = T; static constexpr bool cplx = false; };
+template <> struct Real<float2> { using type = float; static constexpr bool cplx = true; };
+template <> struct Real<double2> { using type = double; static constexpr bool cplx = true; };
+
+__device__ __forceinline__ double fma_ru(double a, double b, double c) { return __fma_ru(a, b, c); }
+__device__ __forceinline__ float fma_ru(float a, float b, float c) { return __fmaf_ru(a, b, c); }
+__device__ __forceinline__ double add_ru(double a, double b) { return __dadd_ru(a, b); }
+__device__ __forceinline__ float add_ru(float a, float b) { return __fadd_ru(a, b); }
+__device__ __forceinline__ int ilogb_(double a) { return ilogb(a); }
+__device__ __forceinline__ int ilogb_(float a) { return ilogbf(a); }
+
+// the reference's warp trees (scaling.hpp:48-97): shfl_down by 16, 8, 4, 2, 1
+template <typename R> __device__ __forceinline__ R tree_sum_ru(R v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = add_ru(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename R> __device__ __forceinline__ R tree_max(R v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// reference: vecnorm::compute_sft, scaling.hpp:3373-3383.  A zero vector gets shift 0 (the
+// reference leaves it undefined there; every product with it is exactly 0 either way).
+__device__ __forceinline__ int fast_sft(double amax, double nrm2, float log2M) {
+    if (amax == 0.0) return 0;
+    const int e     = ilogb(nrm2);
+    const float nf  = __double2float_ru(scalbn(nrm2, -e));
+    const int k     = __float2int_rd(__fmaf_rd(-0.51f, __fadd_ru(__log2f(nf), (float)e), log2M));
+    return min(__float2int_rd(log2M - 1.0f), k) - ilogb(amax);
+}
+__device__ __forceinline__ int fast_sft(float amax, float nrm2, float log2M) {
+    if (amax == 0.0f) return 0;
+    const int k = __float2int_rd(__fmaf_rd(-0.51f, __log2f(nrm2), log2M));
+    return min(__float2int_rd(log2M - 1.0f), k) - ilogbf(amax);
+}
+
+template <typename T, typename R>
+__device__ __forceinline__ void accumulate(const T &x, R &amax, R &acc) {
+    if constexpr (Real<T>::cplx) {
+        const R re = fabs(x.x), im = fabs(x.y);
+        amax = fmax(amax, fmax(re, im));
+        acc  = fma_ru(re, re, acc);
+        acc  = fma_ru(im, im, acc);
+    } else {
+        const R a = fabs(x);
+        amax = fmax(amax, a);
+        acc  = fma_ru(a, a, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast-mode shifts, contiguous vectors: one CTA of W threads per vector, literally the reference's
+// thread ownership; loads are coalesced 4/8/16-byte per lane.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int W>
+__global__ void __launch_bounds__(W) fast_shift_contig_kernel(const T *__restrict__ X, size_t ld, size_t len,
+                                                              float log2M, int16_t *__restrict__ out) {
+    using R = typename Real<T>::type;
+    __shared__ R s_max[32];
+    __shared__ R s_sum[32];
+    const T *__restrict__ p = X + (size_t)blockIdx.x * ld;
+    R amax = 0, acc = 0;
+    size_t i = threadIdx.x;
+    // unrolled by 4 to keep several loads in flight; the FMA chain stays in element order
+    for (; i + 3 * (size_t)W < len; i += 4 * (size_t)W) {
+        const T x0 = p[i], x1 = p[i + W], x2 = p[i + 2 * (size_t)W], x3 = p[i + 3 * (size_t)W];
+        accumulate<T, R>(x0, amax, acc);
+        accumulate<T, R>(x1, amax, acc);
+        accumulate<T, R>(x2, amax, acc);
+        accumulate<T, R>(x3, amax, acc);
+    }
+    for (; i < len; i += W) accumulate<T, R>(p[i], amax, acc);
+
+    amax = tree_max(amax);
+    acc  = tree_sum_ru(acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_max[warp] = amax;
+    if (lane == 1) s_sum[warp] = acc;  // lane 1, as the reference
+    __syncthreads();
+    if (warp == 0) {
+        R a = (lane < W / 32) ? s_max[lane] : R(0);
+        R s = (lane < W / 32) ? s_sum[lane] : R(0);
+        a = tree_max(a);
+        s = tree_sum_ru(s);
+        if (lane == 0) out[blockIdx.x] = (int16_t)(-fast_sft(a, s, log2M));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast-mode shifts, strided vectors (rows of a column-major matrix): 32 vectors per CTA, lane ==
+// vector, 16 warps.  Warp w owns the virtual threads [w*W/16, (w+1)*W/16) of every vector, i.e.
+// element i goes to accumulator (i mod W) and is added in increasing i -- the reference's order.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int W>
+__global__ void __launch_bounds__(512) fast_shift_strided_kernel(const T *__restrict__ X, size_t ld, size_t nvec,
+                                                                 size_t len, float log2M, int16_t *__restrict__ out) {
+    using R = typename Real<T>::type;
+    constexpr int Q  = W / 16;   // virtual threads per warp
+    constexpr int NW = W / 32;   // reference warps per vector
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *s_part = reinterpret_cast<R *>(smem_raw);  // [W][33]   partial sums, [virtual thread][vector]
+    R *s_amax = s_part + W * 33;                  // [16][32]
+    R *s_u    = s_amax + 16 * 32;                 // [32][NW]  per reference-warp values
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t vec  = (size_t)blockIdx.x * 32 + lane;
+    const bool active = vec < nvec;
+    const T *__restrict__ p = X + (active ? vec : 0);
+
+    R acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = 0;
+    R amax = 0;
+    if (active) {
+        constexpr int CH = Q < 8 ? Q : 8;  // loads in flight per lane
+        for (size_t base = (size_t)warp * Q; base < len; base += W) {
+#pragma unroll
+            for (int q0 = 0; q0 < Q; q0 += CH) {
+                T x[CH];
+#pragma unroll
+                for (int q = 0; q < CH; ++q)
+                    if (base + q0 + q < len) x[q] = p[(base + q0 + q) * ld];
+#pragma unroll
+                for (int q = 0; q < CH; ++q)
+                    if (base + q0 + q < len) accumulate<T, R>(x[q], amax, acc[q0 + q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s_part[(warp * Q + q) * 33 + lane] = acc[q];
+    s_amax[warp * 32 + lane] = amax;
+    __syncthreads();
+
+    // level 1: for every (vector r, reference warp g) run the reference's tree on the 32 partials
+    for (int t = warp; t < 32 * NW; t += 16) {
+        const int r = t & 31, g = t >> 5;
+        R v = s_part[(g * 32 + lane) * 33 + r];
+        v   = tree_sum_ru(v);
+        if (lane == 1) s_u[r * NW + g] = v;
+    }
+    __syncthreads();
+    // level 2 + shift
+    for (int r = warp; r < 32; r += 16) {
+        R s = (lane < NW) ? s_u[r * NW + lane] : R(0);
+        s   = tree_sum_ru(s);
+        R a = (lane < 16) ? s_amax[lane * 32 + r] : R(0);
+        a   = tree_max(a);
+        const size_t v = (size_t)blockIdx.x * 32 + r;
+        if (lane == 0 && v < nvec) out[v] = (int16_t)(-fast_sft(a, s, log2M));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residue of an integer-valued fp number modulo m_j, symmetric representative, as int8
+// reference: mod_8i, scaling.hpp:215-230 (cast wraps: cvt.rzi.s32.f32 + byte store)
+// ---------------------------------------------------------------------------------------------
+struct ModConst {
+    double neg_m, rcp;
+    float neg_mf, rcpf;
+};
+__device__ __forceinline__ ModConst load_mod(unsigned j) {
+    ModConst c;
+    c.neg_m  = -(double)OZ_MOD[j];
+    c.rcp    = OZ_RCP64[j];
+    c.neg_mf = -(float)OZ_MOD[j];
+    c.rcpf   = OZ_RCP32[j];
+    return c;
+}
+__device__ __forceinline__ int residue(double a, const ModConst &c) {
+    float t = __double2float_rn(fma(rint(__dmul_rn(a, c.rcp)), c.neg_m, a));
+    t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
+    t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
+    return __float2int_rz(t);
+}
+__device__ __forceinline__ int residue(float a, const ModConst &c) {
+    float t = __fmaf_rn(rintf(__fmul_rn(a, c.rcpf)), c.neg_mf, a);
+    t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
+    t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
+    t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
+    return __float2int_rz(t);
+}
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+__device__ __forceinline__ double scale_trunc(double x, int sft) { return trunc(scalbn(x, sft)); }
+__device__ __forceinline__ float scale_trunc(float x, int sft) { return truncf(scalbnf(x, sft)); }
+
+// ---------------------------------------------------------------------------------------------
+// encode, contiguous vectors.  One thread = 4 consecutive k of one vector (the LSU sweet spot:
+// 2 x 16-byte loads in, one 4-byte store per modulus out, every warp store is a full 128-byte line).
+// grid = (ceil(ld8i/4 / 256), nvec)
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) encode_contig_kernel(const R *__restrict__ X, size_t ld, size_t len,
+                                                            const int16_t *__restrict__ sft_neg, unsigned num_moduli,
+                                                            int8_t *__restrict__ out, size_t ld8i, size_t inc) {
+    const size_t vec = blockIdx.y;
+    const size_t g   = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 along k
+    const size_t i0  = g * 4;
+    if (i0 >= ld8i) return;
+    const int sft = -(int)sft_neg[vec];
+    const R *__restrict__ p = X + vec * ld;
+    R v[4];
+    if (i0 + 3 < len && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
+        if constexpr (sizeof(R) == 8) {
+            const double2 a = *reinterpret_cast<const double2 *>(p + i0);
+            const double2 b = *reinterpret_cast<const double2 *>(p + i0 + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+            const float4 a = *reinterpret_cast<const float4 *>(p + i0);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (i0 + e < len) ? p[i0 + e] : R(0);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = scale_trunc(v[e], sft);
+    int8_t *__restrict__ o = out + vec * ld8i + i0;
+    for (unsigned j = 0; j < num_moduli; ++j) {
+        const ModConst c = load_mod(j);
+        *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) =
+            pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode, strided vectors: tile of 32 vectors x 128 k.  Load with lane == vector (256-byte
+// contiguous segments), scale + truncate, park in shared memory with a rotation that makes both
+// the column-wise writes and the row-wise reads conflict-free, then each thread encodes 16
+// consecutive k of one vector and stores 16 bytes per modulus (a warp writes 4 full 128-byte lines).
+// grid = (ceil(ld8i/128), ceil(nvec/32)), 256 threads
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) encode_strided_kernel(const R *__restrict__ X, size_t ld, size_t nvec, size_t len,
+                                                             const int16_t *__restrict__ sft_neg, unsigned num_moduli,
+                                                             int8_t *__restrict__ out, size_t ld8i, size_t inc) {
+    __shared__ R tile[128 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t v0 = (size_t)blockIdx.y * 32;
+    const size_t k0 = (size_t)blockIdx.x * 128;
+    {
+        const size_t vec = v0 + lane;
+        const bool active = vec < nvec;
+        const int sft = active ? -(int)sft_neg[vec] : 0;
+        const R *__restrict__ p = X + (active ? vec : 0);
+#pragma unroll 4
+        for (int kk = warp; kk < 128; kk += 8) {
+            const size_t k = k0 + kk;
+            R x = (active && k < len) ? p[k * ld] : R(0);
+            tile[kk * 32 + ((lane + 4 * (kk >> 4)) & 31)] = scale_trunc(x, sft);
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 3, g = threadIdx.x & 7;  // vector in tile, 16-wide k group
+    const size_t vec = v0 + r;
+    const size_t kb  = k0 + 16 * g;
+    if (vec >= nvec || kb >= ld8i) return;
+    R v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = tile[(16 * g + e) * 32 + ((r + 4 * g) & 31)];
+    int8_t *__restrict__ o = out + vec * ld8i + kb;
+    for (unsigned j = 0; j < num_moduli; ++j) {
+        const ModConst c = load_mod(j);
+        uint4 w;
+        w.x = pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
+        w.y = pack4(residue(v[4], c), residue(v[5], c), residue(v[6], c), residue(v[7], c));
+        w.z = pack4(residue(v[8], c), residue(v[9], c), residue(v[10], c), residue(v[11], c));
+        w.w = pack4(residue(v[12], c), residue(v[13], c), residue(v[14], c), residue(v[15], c));
+        *reinterpret_cast<uint4 *>(o + (size_t)j * inc) = w;  // ld8i % 16 == 0 and kb % 16 == 0
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// accurate mode, step 1: amax -> sft0 = 5 - ilogb(amax); bound slice = ceil(|x| * 2^sft0) (<= 64)
+// reference: extract_A8i_kernel / extract_B8i_kernel, scaling.hpp:1897-1941, :2215-2260
+// Two kernels: amax per vector (exact, order-free), then the element-wise extraction.
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) amax_contig_kernel(const R *__restrict__ X, size_t ld, size_t len,
+                                                          int16_t *__restrict__ sft0) {
+    __shared__ R s_max[8];
+    const R *__restrict__ p = X + (size_t)blockIdx.x * ld;
+    R amax = 0;
+    for (size_t i = threadIdx.x; i < len; i += 256) amax = fmax(amax, fabs(p[i]));
+    amax = tree_max(amax);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        R a = (threadIdx.x < 8) ? s_max[threadIdx.x] : R(0);
+        a   = tree_max(a);
+        if (threadIdx.x == 0) sft0[blockIdx.x] = (a == R(0)) ? (int16_t)0 : (int16_t)(5 - ilogb_(a));
+    }
+}
+template <typename R>
+__global__ void __launch_bounds__(512) amax_strided_kernel(const R *__restrict__ X, size_t ld, size_t nvec, size_t len,
+                                                           int16_t *__restrict__ sft0) {
+    __shared__ R s_max[16 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t vec = (size_t)blockIdx.x * 32 + lane;
+    R amax = 0;
+    if (vec < nvec) {
+        const R *__restrict__ p = X + vec;
+        for (size_t i = warp; i < len; i += 16) amax = fmax(amax, fabs(p[i * ld]));
+    }
+    s_max[warp * 32 + lane] = amax;
+    __syncthreads();
+    if (warp == 0 && vec < nvec) {
+        R a = 0;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) a = fmax(a, s_max[w * 32 + lane]);
+        sft0[vec] = (a == R(0)) ? (int16_t)0 : (int16_t)(5 - ilogb_(a));
+    }
+}
+__device__ __forceinline__ int bound_int(double x, int sft) { return __double2int_ru(scalbn(fabs(x), sft)); }
+__device__ __forceinline__ int bound_int(float x, int sft) { return __float2int_ru(scalbnf(fabsf(x), sft)); }
+
+template <typename R>
+__global__ void __launch_bounds__(256) bound_contig_kernel(const R *__restrict__ X, size_t ld, size_t len,
+                                                           const int16_t *__restrict__ sft0, int8_t *__restrict__ out,
+                                                           size_t ld8i) {
+    const size_t vec = blockIdx.y;
+    const size_t i0  = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= ld8i) return;
+    const int sft = sft0[vec];
+    const R *__restrict__ p = X + vec * ld;
+    int b[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) b[e] = (i0 + e < len) ? bound_int(p[i0 + e], sft) : 0;
+    *reinterpret_cast<uint32_t *>(out + vec * ld8i + i0) = pack4(b[0], b[1], b[2], b[3]);
+}
+template <typename R>
+__global__ void __launch_bounds__(256) bound_strided_kernel(const R *__restrict__ X, size_t ld, size_t nvec, size_t len,
+                                                            const int16_t *__restrict__ sft0, int8_t *__restrict__ out,
+                                                            size_t ld8i) {
+    __shared__ int8_t tile[32][128 + 16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t v0 = (size_t)blockIdx.y * 32, k0 = (size_t)blockIdx.x * 128;
+    {
+        const size_t vec = v0 + lane;
+        const bool active = vec < nvec;
+        const int sft = active ? (int)sft0[vec] : 0;
+        const R *__restrict__ p = X + (active ? vec : 0);
+        for (int kk = warp; kk < 128; kk += 8) {
+            const size_t k = k0 + kk;
+            tile[lane][kk] = (int8_t)((active && k < len) ? bound_int(p[k * ld], sft) : 0);
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 3, g = threadIdx.x & 7;
+    const size_t vec = v0 + r, kb = k0 + 16 * g;
+    if (vec >= nvec || kb >= ld8i) return;
+    *reinterpret_cast<uint4 *>(out + vec * ld8i + kb) = *reinterpret_cast<const uint4 *>(&tile[r][16 * g]);
+}
+
+// accurate mode, step 3 (reference: int8tc::compute_sft, scaling.hpp:1504-1506)
+__global__ void accurate_shift_kernel(size_t nvec, const int32_t *__restrict__ cmax, float log2M,
+                                      int16_t *__restrict__ sft) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvec) return;
+    const int s0 = sft[v];
+    const int cm = cmax[v];
+    // cmax == 0 (a zero vector, or every partner vector is zero): any shift gives exact zeros; keep
+    // the 6-bit one (the reference evaluates log2(0) here and stores an unspecified shift)
+    const int s  = (cm <= 0) ? s0 : s0 + __float2int_rd(__fmaf_rd(-0.51f, __log2f(__int2float_rn(cm)), log2M));
+    sft[v]       = (int16_t)(-s);
+}
+
+template <typename T, int W>
+cudaError_t run_fast_shifts(bool strided, const void *X, size_t ld, size_t nvec, size_t len, float log2M,
+                            int16_t *out, cudaStream_t st) {
+    using R = typename Real<T>::type;
+    if (nvec == 0) return cudaSuccess;
+    if (strided) {
+        const size_t smem = sizeof(R) * (W * 33 + 16 * 32 + 32 * (W / 32));
+        auto kern = fast_shift_strided_kernel<T, W>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)((nvec + 31) / 32), 512, smem, st>>>(static_cast<const T *>(X), ld, nvec, len, log2M, out);
+    } else {
+        fast_shift_contig_kernel<T, W><<<(unsigned)nvec, W, 0, st>>>(static_cast<const T *>(X), ld, len, log2M, out);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_fast_shifts(int dtype, bool strided, const void *X, size_t ld, size_t nvec, size_t len,
+                               int ref_width, float log2M, int16_t *sft_out, cudaStream_t st) {
+    const bool w512 = ref_width == 512;
+    switch (dtype) {
+        case DT_F64: return run_fast_shifts<double, 128>(strided, X, ld, nvec, len, log2M, sft_out, st);  // 512 only occurs for gemm<float>
+        case DT_F32: return w512 ? run_fast_shifts<float, 512>(strided, X, ld, nvec, len, log2M, sft_out, st)
+                                 : run_fast_shifts<float, 128>(strided, X, ld, nvec, len, log2M, sft_out, st);
+        case DT_C64: return run_fast_shifts<double2, 128>(strided, X, ld, nvec, len, log2M, sft_out, st);
+        case DT_C32: return run_fast_shifts<float2, 128>(strided, X, ld, nvec, len, log2M, sft_out, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename R>
+static cudaError_t run_encode(bool strided, const void *X, size_t ld, size_t nvec, size_t len, const int16_t *sft_neg,
+                              unsigned num_moduli, int8_t *out, size_t ld8i, size_t inc, cudaStream_t st) {
+    if (nvec == 0) return cudaSuccess;
+    if (strided) {
+        dim3 grid((unsigned)((ld8i + 127) / 128), (unsigned)((nvec + 31) / 32));
+        encode_strided_kernel<R><<<grid, 256, 0, st>>>(static_cast<const R *>(X), ld, nvec, len, sft_neg, num_moduli,
+                                                       out, ld8i, inc);
+    } else {
+        // blockIdx.y is limited to 65535: walk the vectors in slabs
+        for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
+            const size_t nv = nvec - v0 < 65535 ? nvec - v0 : 65535;
+            dim3 grid((unsigned)((ld8i / 4 + 255) / 256), (unsigned)nv);
+            encode_contig_kernel<R><<<grid, 256, 0, st>>>(static_cast<const R *>(X) + v0 * ld, ld, len, sft_neg + v0,
+                                                          num_moduli, out + v0 * ld8i, ld8i, inc);
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode(int dtype, bool strided, const void *X, size_t ld, size_t nvec, size_t len,
+                          const int16_t *sft_neg, unsigned num_moduli, int8_t *out, size_t ld8i, size_t inc,
+                          cudaStream_t st) {
+    if (strided && (nvec + 31) / 32 > 65535) return cudaErrorInvalidValue;
+    switch (dtype) {
+        case DT_F64: return run_encode<double>(strided, X, ld, nvec, len, sft_neg, num_moduli, out, ld8i, inc, st);
+        case DT_F32: return run_encode<float>(strided, X, ld, nvec, len, sft_neg, num_moduli, out, ld8i, inc, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename R>
+static cudaError_t run_bound(bool strided, const void *X, size_t ld, size_t nvec, size_t len, int8_t *out, size_t ld8i,
+                             int16_t *sft0, cudaStream_t st) {
+    if (nvec == 0) return cudaSuccess;
+    const R *x = static_cast<const R *>(X);
+    if (strided) {
+        amax_strided_kernel<R><<<(unsigned)((nvec + 31) / 32), 512, 0, st>>>(x, ld, nvec, len, sft0);
+        dim3 grid((unsigned)((ld8i + 127) / 128), (unsigned)((nvec + 31) / 32));
+        bound_strided_kernel<R><<<grid, 256, 0, st>>>(x, ld, nvec, len, sft0, out, ld8i);
+    } else {
+        amax_contig_kernel<R><<<(unsigned)nvec, 256, 0, st>>>(x, ld, len, sft0);
+        for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
+            const size_t nv = nvec - v0 < 65535 ? nvec - v0 : 65535;
+            dim3 grid((unsigned)((ld8i / 4 + 255) / 256), (unsigned)nv);
+            bound_contig_kernel<R><<<grid, 256, 0, st>>>(x + v0 * ld, ld, len, sft0 + v0, out + v0 * ld8i, ld8i);
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bound_extract(int dtype, bool strided, const void *X, size_t ld, size_t nvec, size_t len,
+                                 int8_t *out8i, size_t ld8i, int16_t *sft_out, cudaStream_t st) {
+    switch (dtype) {
+        case DT_F64: return run_bound<double>(strided, X, ld, nvec, len, out8i, ld8i, sft_out, st);
+        case DT_F32: return run_bound<float>(strided, X, ld, nvec, len, out8i, ld8i, sft_out, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_accurate_shifts(size_t nvec, const int32_t *cmax, float log2M, int16_t *sft_inout,
+                                   cudaStream_t st) {
+    if (nvec == 0) return cudaSuccess;
+    accurate_shift_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(nvec, cmax, log2M, sft_inout);
+    return cudaGetLastError();
+}
+
+}  // namespace oz
