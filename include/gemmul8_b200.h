@@ -122,6 +122,9 @@ int gemmul8_b200_product_i32(const gemmul8_b200_args *args, unsigned j, int32_t 
 int gemmul8_b200_modulus(unsigned j);                /* m_j, j in 0..19 */
 double gemmul8_b200_crt_weight(unsigned num_moduli, unsigned j, int part /*0=single,1=hi,2=lo*/);
 
+/* Number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches). */
+unsigned long long gemmul8_b200_launch_count(void);
+
 const char *gemmul8_b200_last_error(void);
 const char *gemmul8_b200_version(void);
 

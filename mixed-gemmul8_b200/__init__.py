@@ -26,7 +26,7 @@ FLAG_TIMERS, FLAG_STAGE_SCALING, FLAG_STAGE_RESIDUES, FLAG_GEMM_SIMT = 1, 1 << 4
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",
     "gemmul8_b200_gemm_host", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
-    "gemmul8_b200_last_error", "gemmul8_b200_version",
+    "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
 )
 
 
@@ -87,6 +87,7 @@ def lib():
         L.gemmul8_b200_modulus.argtypes = [C.c_uint]
         L.gemmul8_b200_crt_weight.restype = C.c_double
         L.gemmul8_b200_crt_weight.argtypes = [C.c_uint, C.c_uint, C.c_int]
+        L.gemmul8_b200_launch_count.restype = C.c_ulonglong
         L.gemmul8_b200_last_error.restype = C.c_char_p
         L.gemmul8_b200_version.restype = C.c_char_p
         _lib = L
@@ -210,6 +211,11 @@ def work_views(work, L, num_moduli, m, n):
     v["sftA"] = work[L.off_sftA:L.off_sftA + 2 * m].view(torch.int16)
     v["sftB"] = work[L.off_sftB:L.off_sftB + 2 * n].view(torch.int16)
     return v
+
+
+def launch_count():
+    """Kernels launched by the library so far (process-wide)."""
+    return lib().gemmul8_b200_launch_count()
 
 
 def modulus(j):

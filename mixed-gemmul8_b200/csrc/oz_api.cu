@@ -12,9 +12,15 @@
 #include "../../include/gemmul8_b200.h"
 #include "oz_common.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
+
+namespace oz {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace oz
 
 namespace {
 
@@ -283,6 +289,8 @@ double gemmul8_b200_crt_weight(unsigned N, unsigned j, int part) {
     if (N < 8) return 0.0;
     return part == 1 ? oz::host_tab::OZ_W2_HI[N - 8][j] : oz::host_tab::OZ_W2_LO[N - 8][j];
 }
+
+unsigned long long gemmul8_b200_launch_count(void) { return oz::g_launches.load(std::memory_order_relaxed); }
 
 const char *gemmul8_b200_last_error(void) { return g_last_error.c_str(); }
 const char *gemmul8_b200_version(void) { return "gemmul8_b200 0.1 (sm_100a, tcgen05 kind::i8)"; }

@@ -100,6 +100,7 @@ cudaError_t run_crt(bool split, unsigned N, size_t m, size_t n, const uint8_t *C
     dim3 block(64, 4), grid((unsigned)(((m + 3) / 4 + 63) / 64), (unsigned)((n + 3) / 4));
     if (split) crt_kernel<T, true><<<grid, block, 0, st>>>(N, m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta);
     else       crt_kernel<T, false><<<grid, block, 0, st>>>(N, m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta);
+    count_launch();
     return cudaGetLastError();
 }
 

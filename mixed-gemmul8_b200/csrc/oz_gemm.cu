@@ -412,6 +412,7 @@ cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
     kern<<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(ma, mb, a);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -420,6 +421,7 @@ cudaError_t launch_simt_t(const GemmProblem &p, cudaStream_t st) {
     KernelArgs a = make_args(p);
     dim3 block(32, 8), grid((unsigned)((p.rowsA + 31) / 32), (unsigned)((p.rowsB + 7) / 8), p.num_slices);
     oz_gemm_simt_kernel<EPI><<<grid, block, 0, st>>>(p.A8i, p.B8i, p.sizeA, p.sizeB, p.ld8i, a);
+    count_launch();
     return cudaGetLastError();
 }
 

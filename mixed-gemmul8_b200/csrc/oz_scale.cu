@@ -412,6 +412,7 @@ cudaError_t run_fast_shifts(bool strided, const void *X, size_t ld, size_t nvec,
     } else {
         fast_shift_contig_kernel<T, W><<<(unsigned)nvec, W, 0, st>>>(static_cast<const T *>(X), ld, len, log2M, out);
     }
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -438,6 +439,7 @@ static cudaError_t run_encode(bool strided, const void *X, size_t ld, size_t nve
         dim3 grid((unsigned)((ld8i + 127) / 128), (unsigned)((nvec + 31) / 32));
         encode_strided_kernel<R><<<grid, 256, 0, st>>>(static_cast<const R *>(X), ld, nvec, len, sft_neg, num_moduli,
                                                        out, ld8i, inc);
+        count_launch();
     } else {
         // blockIdx.y is limited to 65535: walk the vectors in slabs
         for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
@@ -445,6 +447,7 @@ static cudaError_t run_encode(bool strided, const void *X, size_t ld, size_t nve
             dim3 grid((unsigned)((ld8i / 4 + 255) / 256), (unsigned)nv);
             encode_contig_kernel<R><<<grid, 256, 0, st>>>(static_cast<const R *>(X) + v0 * ld, ld, len, sft_neg + v0,
                                                           num_moduli, out + v0 * ld8i, ld8i, inc);
+            count_launch();
         }
     }
     return cudaGetLastError();
@@ -470,12 +473,15 @@ static cudaError_t run_bound(bool strided, const void *X, size_t ld, size_t nvec
         amax_strided_kernel<R><<<(unsigned)((nvec + 31) / 32), 512, 0, st>>>(x, ld, nvec, len, sft0);
         dim3 grid((unsigned)((ld8i + 127) / 128), (unsigned)((nvec + 31) / 32));
         bound_strided_kernel<R><<<grid, 256, 0, st>>>(x, ld, nvec, len, sft0, out, ld8i);
+        count_launch(2);
     } else {
         amax_contig_kernel<R><<<(unsigned)nvec, 256, 0, st>>>(x, ld, len, sft0);
+        count_launch();
         for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
             const size_t nv = nvec - v0 < 65535 ? nvec - v0 : 65535;
             dim3 grid((unsigned)((ld8i / 4 + 255) / 256), (unsigned)nv);
             bound_contig_kernel<R><<<grid, 256, 0, st>>>(x + v0 * ld, ld, len, sft0 + v0, out + v0 * ld8i, ld8i);
+            count_launch();
         }
     }
     return cudaGetLastError();
@@ -494,6 +500,7 @@ cudaError_t launch_accurate_shifts(size_t nvec, const int32_t *cmax, float log2M
                                    cudaStream_t st) {
     if (nvec == 0) return cudaSuccess;
     accurate_shift_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(nvec, cmax, log2M, sft_inout);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -1,0 +1,92 @@
+"""2-D block decomposition of C across the GPUs of one node (NEW relative to the reference, which is
+single-GPU).
+
+The emulation shards with no data-path reduction: shifts are per row of op(A) over all k and per
+column of op(B) over all k, residues and the CRT are element-wise, so rank (p, q) of a P x Q grid
+only needs row panel p of A and column panel q of B, and K is never split.  The only exchange is
+the panel distribution: every rank starts with a 1/Q slice of its A row panel and a 1/P slice of
+its B column panel (HPL-like ownership), and the panels are assembled with NCCL all-gathers over
+NVLink inside grid rows / grid columns.  Each rank then runs the single-GPU path on its C block
+(FP64 panels travel at 8 B/element; shipping 14 int8 slices would cost 14 B/element, and the
+redundant encode is ~1% of the GEMM time).
+
+`BlockGrid` works on the gloo backend too (CPU tests exercise the index algebra and the collectives
+with world_size 2); the compute call itself needs CUDA.
+"""
+import torch
+import torch.distributed as dist
+
+
+def grid_shape(world):
+    """P x Q with P <= Q and P*Q == world (1x1, 1x2, 2x2, 2x4, ...)."""
+    p = 1
+    while (p * 2) * (p * 2) <= world:
+        p *= 2
+    while world % p:
+        p -= 1
+    return p, world // p
+
+
+class BlockGrid:
+    def __init__(self, world=None, rank=None):
+        self.world = dist.get_world_size() if world is None else world
+        self.rank = dist.get_rank() if rank is None else rank
+        self.P, self.Q = grid_shape(self.world)
+        self.p, self.q = divmod(self.rank, self.Q)
+        self.row_group = self.col_group = None
+        if dist.is_initialized() and self.world > 1:
+            # every rank must create every group, in the same order
+            for pp in range(self.P):
+                grp = dist.new_group([pp * self.Q + qq for qq in range(self.Q)])
+                if pp == self.p:
+                    self.row_group = grp
+            for qq in range(self.Q):
+                grp = dist.new_group([pp * self.Q + qq for pp in range(self.P)])
+                if qq == self.q:
+                    self.col_group = grp
+
+    # -- ownership -------------------------------------------------------------------------
+    def block_dims(self, m, n):
+        """Rows / columns of the C block of this rank (m, n must divide evenly)."""
+        assert m % self.P == 0 and n % self.Q == 0
+        return m // self.P, n // self.Q
+
+    def a_slice_k(self, k):
+        """k-range [lo, hi) of A's row panel p that this rank owns before the exchange."""
+        assert k % self.Q == 0
+        w = k // self.Q
+        return self.q * w, (self.q + 1) * w
+
+    def b_slice_cols(self, n_loc):
+        """column range [lo, hi) of B's column panel q (n_loc columns) owned before the exchange."""
+        assert n_loc % self.P == 0
+        w = n_loc // self.P
+        return self.p * w, (self.p + 1) * w
+
+    # -- panel exchange --------------------------------------------------------------------
+    def gather_a_panel(self, a_slice, m_loc, k):
+        """a_slice: (k/Q, m_loc) tensor = column-major m_loc x k/Q block.  Returns the (k, m_loc) panel."""
+        if self.Q == 1:
+            return a_slice
+        out = torch.empty((k, m_loc), dtype=a_slice.dtype, device=a_slice.device)
+        dist.all_gather_into_tensor(out, a_slice.contiguous(), group=self.row_group)
+        return out
+
+    def gather_b_panel(self, b_slice, n_loc, k):
+        """b_slice: (n_loc/P, k) tensor = column-major k x n_loc/P block.  Returns the (n_loc, k) panel."""
+        if self.P == 1:
+            return b_slice
+        out = torch.empty((n_loc, k), dtype=b_slice.dtype, device=b_slice.device)
+        dist.all_gather_into_tensor(out, b_slice.contiguous(), group=self.col_group)
+        return out
+
+
+def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli, fastmode, work, flags=0):
+    """C_block(p,q) = alpha * A_panel(p) * B_panel(q) + beta * C_block, ops N/N, all column-major.
+
+    a_slice / b_slice are this rank's pre-exchange pieces (see BlockGrid); returns the phase timers."""
+    m_loc, n_loc = grid.block_dims(m, n)
+    a_panel = grid.gather_a_panel(a_slice, m_loc, k)
+    b_panel = grid.gather_b_panel(b_slice, n_loc, k)
+    return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
+                    num_moduli, fastmode, work, flags=flags)
