@@ -233,7 +233,7 @@ def main():
     peak = 2.0 * (bf16_sust if long_step else bf16_burst)
     ach = per_gpu_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                       "traffic": None, "kernel": "oz_gemm_tcgen05_kernel<EPI_RESIDUE>", "kernel_ms": gemm_ms,
+                       "traffic": None, "kernel": "oz_gemm_tcgen05_kernel<EPI_RESIDUE> (all moduli, residues fused)", "kernel_ms": gemm_ms,
                        "peak_source": f"2 x bf16 {'sustained' if long_step else 'burst'} of {peak_src}: kind::i8 issues at twice the bf16 rate",
                        "algorithmic_ops": "2*N*m*n*k int8 ops per launch"}
     enc_bytes = (8.0 * (m * k + k * n) * 2 + N * (m * k + k * n)) / world  # two passes over fp64 inputs + int8 slices out

@@ -56,6 +56,7 @@ enum {
     GEMMUL8_FLAG_TIMERS = 1u, /* bracket the 4 phases with CUDA events and fill timers_ns (synchronises) */
     GEMMUL8_FLAG_STAGE_SCALING  = 1u << 4, /* run only phase 0: shifts + residue slices (parity tests) */
     GEMMUL8_FLAG_STAGE_RESIDUES = 1u << 5, /* run phases 0-2: ... + per-modulus products mod m_j      */
+    GEMMUL8_FLAG_FUSED_CRT      = 1u << 6, /* one kernel for GEMM + residues + CRT (tile-major schedule) */
     GEMMUL8_FLAG_GEMM_SIMT      = 1u << 8  /* debug: use the CUDA-core int8 GEMM instead of tcgen05   */
 };
 
@@ -77,7 +78,8 @@ typedef struct {
     unsigned flags;
     double timers_ns[4];       /* out: {scaling, int8 GEMM, int32->residue, inverse scaling} in ns
                                   (reference returns the same 4 numbers, gemmul8.cu:17,291).  The
-                                  residue reduction is fused into the GEMM epilogue here, so [2] = 0. */
+                                  residue reduction is fused into the GEMM epilogue here, so [2] = 0
+                                  (with GEMMUL8_FLAG_FUSED_CRT also [3] = 0: [1] covers all three). */
 } gemmul8_b200_args;
 
 /* Byte offsets of the sub-buffers inside `work`; identical to the reference's carve

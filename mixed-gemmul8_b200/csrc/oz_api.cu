@@ -177,16 +177,29 @@ int gemm_real(gemmul8_b200_args *a) {
     timer.mark();
     if (a->flags & GEMMUL8_FLAG_STAGE_SCALING) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
 
-    // ---------------- phases 1+2: all-moduli int8 GEMM with fused residue reduction ----------------
+    // ---------------- phases 1+2 (+3): all-moduli int8 GEMM with the residue reduction in its epilogue ----------------
+    const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;  // numM == 2 (N >= 8) and fp64 out
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.B8i = B8i; gp.rowsA = m; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
     gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    // Default: item-major GEMM + the stand-alone CRT kernel.  The single-kernel variant (every CTA walks all
+    // moduli of its tile, CRT warps behind the last modulus) is kept behind GEMMUL8_FLAG_FUSED_CRT: on
+    // B200 its tile-major schedule costs more L2 misses than the CRT pass saves ("What was tried").
+    const bool staged = simt || (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) != 0 || (a->flags & GEMMUL8_FLAG_FUSED_CRT) == 0;
+    if (!staged) {
+        gp.C = a->C; gp.ldc = a->ldc; gp.dtype_C = a->dtype_C; gp.split_weights = split; gp.sftA = sftA; gp.sftB = sftB;
+        if (a->dtype_C == GEMMUL8_F64) { gp.alpha = *static_cast<const double *>(a->alpha); gp.beta = *static_cast<const double *>(a->beta); }
+        else                           { gp.alpha = *static_cast<const float *>(a->alpha);  gp.beta = *static_cast<const float *>(a->beta); }
+        OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_CRT, st), "int8 gemm + crt");
+        timer.mark();
+        timer.finish(a->timers_ns);
+        return GEMMUL8_OK;
+    }
     OZ_CUDA(gemm(gp, oz::EPI_RESIDUE, st), "int8 gemm");
     timer.mark();
     if (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
 
     // ---------------- phase 3: CRT + inverse scaling ----------------
-    const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;  // numM == 2 (N >= 8) and fp64 out
     OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, n, C8u, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, st), "crt");
     timer.mark();
     timer.finish(a->timers_ns);

@@ -11,82 +11,68 @@
 //
 // Layout: one thread = 4 consecutive rows of one column.  A warp reads 128 contiguous residue
 // bytes per modulus and writes 1 KiB (fp64) of C; all N residue loads are issued before use.
-#include "oz_common.cuh"
+#include "oz_crt.cuh"
 
 namespace oz {
 namespace {
 
-template <typename T> __device__ __forceinline__ T cast_out(double v);
-template <> __device__ __forceinline__ double cast_out<double>(double v) { return v; }
-template <> __device__ __forceinline__ float cast_out<float>(double v) { return __double2float_rn(v); }
-
-__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
-__device__ __forceinline__ float fma_t(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-
-enum AlphaBeta : int { AB_10 = 0, AB_11, AB_1B, AB_A0, AB_A1, AB_AB };
-
-template <typename T>
-__device__ __forceinline__ T combine(int mode, T alpha, T beta, T c, const T *cptr) {
-    switch (mode) {
-        case AB_10: return c;
-        case AB_11: return c + *cptr;
-        case AB_1B: return fma_t(beta, *cptr, c);
-        case AB_A0: return alpha * c;
-        case AB_A1: return fma_t(alpha, c, *cptr);
-        default:    return fma_t(beta, *cptr, alpha * c);
-    }
-}
-
-template <typename T, bool SPLIT>
-__global__ void __launch_bounds__(256) crt_kernel(unsigned num_moduli, size_t m, size_t n,
-                                                  const uint8_t *__restrict__ C8u, size_t ldc8u, size_t sizeC,
-                                                  T *__restrict__ C, size_t ldc, const int16_t *__restrict__ sftA,
-                                                  const int16_t *__restrict__ sftB, int mode, T alpha, T beta) {
+// N is a compile-time constant: the modulus loop unrolls completely, the CRT weights become
+// constant-bank operands of the DFMAs and all N residue loads are issued before the first use.
+template <typename T, bool SPLIT, int N>
+__global__ void __launch_bounds__(256) crt_kernel(size_t m, size_t n, const uint8_t *__restrict__ C8u, size_t ldc8u,
+                                                  size_t sizeC, T *__restrict__ C, size_t ldc,
+                                                  const int16_t *__restrict__ sftA, const int16_t *__restrict__ sftB,
+                                                  int mode, T alpha, T beta) {
     const size_t row0 = ((size_t)blockIdx.x * 64 + threadIdx.x) * 4;
     const size_t col  = (size_t)blockIdx.y * 4 + threadIdx.y;
     if (row0 >= m || col >= n) return;
-    const unsigned ti = num_moduli - 2;
-
-    uint32_t res[kMaxModuli];
+    uint32_t res[N];
     const uint8_t *__restrict__ src = C8u + col * ldc8u + row0;
 #pragma unroll
-    for (int j = 0; j < kMaxModuli; ++j)
-        if (j < (int)num_moduli) res[j] = *reinterpret_cast<const uint32_t *>(src + (size_t)j * sizeC);
+    for (int j = 0; j < N; ++j) res[j] = *reinterpret_cast<const uint32_t *>(src + (size_t)j * sizeC);
 
     double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int j = 0; j < kMaxModuli; ++j) {
-        if (j < (int)num_moduli) {
-            double w1, w2 = 0.0;
-            if constexpr (SPLIT) { w1 = dev_tab::OZ_W2_HI[num_moduli - 8][j]; w2 = dev_tab::OZ_W2_LO[num_moduli - 8][j]; }
-            else { w1 = dev_tab::OZ_W1[ti][j]; }
+    for (int j = 0; j < N; ++j) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double r = __uint2double_rn((res[j] >> (8 * e)) & 0xffu);
-                s1[e] = fma(w1, r, s1[e]);
-                if constexpr (SPLIT) s2[e] = fma(w2, r, s2[e]);
-            }
-        }
+        for (int e = 0; e < 4; ++e) crt_step<SPLIT>(N, j, __byte_perm(res[j], 0, 0x4440 + e), s1[e], s2[e]);
     }
-    const double invM = dev_tab::OZ_INV_M[ti], M1 = dev_tab::OZ_M_HI[ti], M2 = dev_tab::OZ_M_LO[ti];
     const int sb = sftB[col];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const size_t row = row0 + e;
-        if (row >= m) break;
-        double c;
-        if constexpr (SPLIT) {
-            const double quot = -rint(fma(s1[e], invM, s2[e] * invM));
-            const double t1   = fma(quot, M1, s1[e]) + s2[e];
-            c                 = fma(quot, M2, t1);
+    T *cptr = C + col * ldc + row0;
+    if (row0 + 3 < m) {
+        int sa[4];
+        if ((reinterpret_cast<uintptr_t>(sftA + row0) & 7) == 0) {
+            const short4 s4 = *reinterpret_cast<const short4 *>(sftA + row0);
+            sa[0] = s4.x; sa[1] = s4.y; sa[2] = s4.z; sa[3] = s4.w;
         } else {
-            const double quot = -rint(s1[e] * invM);
-            c                 = fma(quot, M1, s1[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sa[e] = sftA[row0 + e];
         }
-        c = scalbn(c, (int)sftA[row] + sb);
-        T *cptr = C + col * ldc + row;
-        *cptr   = combine<T>(mode, alpha, beta, cast_out<T>(c), cptr);
+        T out[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            out[e] = combine<T>(mode, alpha, beta, cast_out<T>(scale_pow2(crt_finish<SPLIT>(N, s1[e], s2[e]), sa[e] + sb)), cptr + e);
+        if ((reinterpret_cast<uintptr_t>(cptr) & (4 * sizeof(T) - 1)) == 0) {
+            if constexpr (sizeof(T) == 8) {
+                reinterpret_cast<double2 *>(cptr)[0] = make_double2(out[0], out[1]);
+                reinterpret_cast<double2 *>(cptr)[1] = make_double2(out[2], out[3]);
+            } else {
+                *reinterpret_cast<float4 *>(cptr) = make_float4(out[0], out[1], out[2], out[3]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cptr[e] = out[e];
+        }
+    } else {
+        for (int e = 0; e < 4 && row0 + e < m; ++e)
+            cptr[e] = combine<T>(mode, alpha, beta, cast_out<T>(scale_pow2(crt_finish<SPLIT>(N, s1[e], s2[e]), (int)sftA[row0 + e] + sb)), cptr + e);
     }
+}
+
+template <typename T, bool SPLIT, int N>
+void launch_one(dim3 grid, dim3 block, cudaStream_t st, size_t m, size_t n, const uint8_t *C8u, size_t ldc8u, size_t sizeC,
+                void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, int mode, T alpha, T beta) {
+    crt_kernel<T, SPLIT, N><<<grid, block, 0, st>>>(m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta);
 }
 
 template <typename T>
@@ -94,12 +80,22 @@ cudaError_t run_crt(bool split, unsigned N, size_t m, size_t n, const uint8_t *C
                     size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha_host, const void *beta_host,
                     cudaStream_t st) {
     const T alpha = *static_cast<const T *>(alpha_host), beta = *static_cast<const T *>(beta_host);
-    int mode;
-    if (alpha == T(1)) mode = (beta == T(0)) ? AB_10 : (beta == T(1)) ? AB_11 : AB_1B;
-    else               mode = (beta == T(0)) ? AB_A0 : (beta == T(1)) ? AB_A1 : AB_AB;
+    const int mode = alpha_beta_mode(alpha, beta);
     dim3 block(64, 4), grid((unsigned)(((m + 3) / 4 + 63) / 64), (unsigned)((n + 3) / 4));
-    if (split) crt_kernel<T, true><<<grid, block, 0, st>>>(N, m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta);
-    else       crt_kernel<T, false><<<grid, block, 0, st>>>(N, m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta);
+#define OZ_CRT_CASE(NN)                                                                                                          \
+    case NN:                                                                                                                     \
+        if constexpr (NN >= 8 && sizeof(T) == 8) {                                                                               \
+            if (split) { launch_one<T, true, NN>(grid, block, st, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta); break; } \
+        }                                                                                                                        \
+        launch_one<T, false, NN>(grid, block, st, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta);               \
+        break;
+    switch (N) {
+        OZ_CRT_CASE(2) OZ_CRT_CASE(3) OZ_CRT_CASE(4) OZ_CRT_CASE(5) OZ_CRT_CASE(6) OZ_CRT_CASE(7) OZ_CRT_CASE(8)
+        OZ_CRT_CASE(9) OZ_CRT_CASE(10) OZ_CRT_CASE(11) OZ_CRT_CASE(12) OZ_CRT_CASE(13) OZ_CRT_CASE(14) OZ_CRT_CASE(15)
+        OZ_CRT_CASE(16) OZ_CRT_CASE(17) OZ_CRT_CASE(18) OZ_CRT_CASE(19) OZ_CRT_CASE(20)
+        default: return cudaErrorInvalidValue;
+    }
+#undef OZ_CRT_CASE
     count_launch();
     return cudaGetLastError();
 }

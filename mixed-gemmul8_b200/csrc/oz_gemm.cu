@@ -12,15 +12,29 @@
 //                             accumulators double-buffered in TMEM (2 x 256 columns)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue    : tcgen05.ld (lane == row), Barrett reduction mod m_j, byte stores
-// A work item is (C tile, modulus); items are ordered (band of 16 row-tiles, modulus, column tile,
-// row tile) so that the ~148 items in flight share one modulus and a compact block of A / B panels.
+//   warps 8-11  CRT         : (EPI_CRT) once a tile's last modulus is stored, re-read its residues
+//                             column-wise (128-byte rows per load, 28 loads in flight per lane),
+//                             CRT + mod M + inverse scaling + alpha/beta, 1 KiB stores of C
+// A work item is (C tile, modulus).  Two schedules:
+//   item-major (EPI_RESIDUE / EPI_INT32 / EPI_ABSMAX): items ordered (band of 16 row tiles, modulus,
+//       column tile, row tile); the ~148 items in flight share one modulus and a compact block of panels;
+//   tile-major (EPI_CRT): every CTA walks ALL moduli of its C tile (tiles ordered band / column / row,
+//       so the 148 tiles in flight still form a compact 16 x ~9 block that moves through the moduli
+//       together).  After the last modulus the CTA's four CRT warps read the tile's residue bytes
+//       back (L2-resident: 14 x 32 KiB per CTA), run the CRT accumulation + mod M + inverse scaling
+//       + alpha/beta (reference: GEMMul8/src/inverse_scaling.hpp:35-62,140-172) and write C, while
+//       the TMA / MMA / epilogue warps are already working through the next tile.  No separate CRT
+//       kernel, no second pass over HBM.
 //
 // Both operands are K-major exactly as the reference lays them out (A8i[j][row][k], B8i[j][col][k],
 // row stride lda8i), so a 3-D tensor map (k, row, modulus) serves all moduli and K / row tails are
 // zero-filled by TMA.
 #include "oz_common.cuh"
+#include "oz_crt.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
+#include <cstring>
 #include <cudaTypedefs.h>
 
 namespace oz {
@@ -37,7 +51,7 @@ constexpr int SMEM_STAGE = SMEM_A + SMEM_B;
 constexpr int SMEM_BARRIERS = 256;
 constexpr int SMEM_TOTAL = STAGES * SMEM_STAGE + SMEM_BARRIERS + 1024;  // + slack for 1024-B alignment
 constexpr int BAND_M = 16;  // row tiles per scheduling band
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---------------------------------------------------------------------------------------------
@@ -142,11 +156,32 @@ struct Sched {
 
 struct KernelArgs {
     uint32_t rowsA, rowsB, num_kb, first_modulus;
+    uint32_t tile_major, num_slices;
     Sched sched;
     uint8_t *C8u; size_t ldc8u, sizeC;
     int32_t *C32i; size_t ldc32i;
     int32_t *rowmax; int32_t *colmax;
+    // EPI_CRT
+    void *C; size_t ldc;
+    const int16_t *sftA; const int16_t *sftB;
+    double alpha, beta; int ab_mode; int debug_skip_crt;
 };
+
+// the it-th work item of this CTA; false when the CTA has run out of work
+__device__ __forceinline__ bool next_work(const KernelArgs &a, uint32_t it, uint32_t &tm, uint32_t &tn, uint32_t &j) {
+    uint32_t unit, jj = 0;
+    if (a.tile_major) {
+        const uint32_t t = it / a.num_slices;
+        jj   = it - t * a.num_slices;
+        unit = blockIdx.x + t * gridDim.x;
+    } else {
+        unit = blockIdx.x + it * gridDim.x;
+    }
+    if (unit >= a.sched.total) return false;
+    a.sched.decode(unit, tm, tn, j);
+    j += jj;
+    return true;
+}
 
 // canonical residue in [0, m) of a (possibly wrapped) int32; modulus index 0 is 256
 __device__ __forceinline__ uint32_t reduce_mod(int32_t x, int32_t m, int32_t inv) {
@@ -156,7 +191,7 @@ __device__ __forceinline__ uint32_t reduce_mod(int32_t x, int32_t m, int32_t inv
     return (uint32_t)r;
 }
 
-template <int EPI>
+template <int EPI, typename T = double, bool SPLIT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const KernelArgs args) {
@@ -169,6 +204,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t crt_full_bar = bar_base + 8u * (2 * STAGES + 5), crt_empty_bar = bar_base + 8u * (2 * STAGES + 6);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,6 +216,8 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        mbar_init(crt_full_bar, 128);
+        mbar_init(crt_empty_bar, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -191,16 +229,13 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const uint32_t total = args.sched.total;
     const uint32_t num_kb = args.num_kb;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
-                uint32_t tm, tn, j;
-                args.sched.decode(item, tm, tn, j);
+            uint32_t stage = 0, phase = 0, tm, tn, j;
+            for (uint32_t it = 0; next_work(args, it, tm, tn, j); ++it) {
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * SMEM_STAGE;
@@ -215,8 +250,8 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-            uint32_t stage = 0, phase = 0, it = 0;
-            for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+            uint32_t stage = 0, phase = 0, tm, tn, j;
+            for (uint32_t it = 0; next_work(args, it, tm, tn, j); ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tcgen05_fence_after();
@@ -237,13 +272,11 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 tcgen05_commit(tfull_bar(acc));  // accumulator complete
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
-        uint32_t it = 0;
-        for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++it) {
-            uint32_t tm, tn, j;
-            args.sched.decode(item, tm, tn, j);
+        uint32_t tm, tn, j;
+        for (uint32_t it = 0; next_work(args, it, tm, tn, j); ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
@@ -253,11 +286,11 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const bool row_ok   = row < args.rowsA;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
 
-            if constexpr (EPI == EPI_RESIDUE) {
+            if constexpr (EPI == EPI_RESIDUE || EPI == EPI_CRT) {
                 const uint32_t mj  = args.first_modulus + j;
                 const int32_t m    = dev_tab::OZ_MOD[mj];
                 const int32_t inv  = (int32_t)(4294967296ull / (uint32_t)m);
-                uint8_t *__restrict__ out = args.C8u + (size_t)j * args.sizeC + row;
+                uint8_t *out = args.C8u + (size_t)j * args.sizeC + row;  // (re-read below under EPI_CRT: no __restrict__)
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 16) {
                     uint32_t v[16];
@@ -312,7 +345,81 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 if (row_ok && rmax > 0) atomicMax(args.rowmax + row, rmax);
             }
             tcgen05_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            mbar_arrive(tempty_bar(acc));  // the accumulator is free again: the MMA warp runs ahead
+
+            if constexpr (EPI == EPI_CRT) {
+                if (j + 1 == args.num_slices) {
+                    // hand the finished tile to the CRT warps (mbarrier arrive = release, their wait = acquire)
+                    const uint32_t t = it / args.num_slices;
+                    if (t > 0) mbar_wait(crt_empty_bar, (t - 1) & 1);
+                    mbar_arrive(crt_full_bar);
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== CRT warps =====================
+        if constexpr (EPI == EPI_CRT) {
+            const unsigned N = args.num_slices;
+            const int w      = warp - 8;
+            const T alpha = (T)args.alpha, beta = (T)args.beta;
+            uint32_t tm, tn, j;
+            for (uint32_t t = 0; next_work(args, t * N + (N - 1), tm, tn, j); ++t) {
+                mbar_wait(crt_full_bar, t & 1);
+                const uint32_t row0 = tm * BLOCK_M + 4 * lane;
+                const uint32_t col0 = tn * BLOCK_N;
+                const uint32_t ncol = min((uint32_t)BLOCK_N, args.rowsB - col0);
+                if (row0 < args.rowsA && !args.debug_skip_crt) {
+                    int sa[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sa[e] = (row0 + e < args.rowsA) ? (int)args.sftA[row0 + e] : 0;
+                    const uint8_t *res = args.C8u + row0;
+                    T *crow            = static_cast<T *>(args.C) + row0;
+#pragma unroll 1
+                    for (uint32_t c = 2 * w; c < ncol; c += 8) {   // two columns per step and warp
+                        const bool two = c + 1 < ncol;
+                        const uint8_t *src0 = res + (size_t)(col0 + c) * args.ldc8u;
+                        const uint8_t *src1 = src0 + (two ? args.ldc8u : 0);
+                        uint32_t r0[kMaxModuli], r1[kMaxModuli];
+#pragma unroll
+                        for (int jj = 0; jj < kMaxModuli; ++jj) {
+                            if (jj < (int)N) {
+                                r0[jj] = __ldcg(reinterpret_cast<const uint32_t *>(src0 + (size_t)jj * args.sizeC));
+                                r1[jj] = __ldcg(reinterpret_cast<const uint32_t *>(src1 + (size_t)jj * args.sizeC));
+                            }
+                        }
+                        double s1[8], s2[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { s1[e] = 0.0; s2[e] = 0.0; }
+#pragma unroll
+                        for (int jj = 0; jj < kMaxModuli; ++jj) {
+                            if (jj < (int)N) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    crt_step<SPLIT>(N, jj, (r0[jj] >> (8 * e)) & 0xffu, s1[e], s2[e]);
+                                    crt_step<SPLIT>(N, jj, (r1[jj] >> (8 * e)) & 0xffu, s1[4 + e], s2[4 + e]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            if (cc == 0 || two) {
+                                const uint32_t col = col0 + c + cc;
+                                const int sb       = (int)args.sftB[col];
+                                T *cptr            = crow + (size_t)col * args.ldc;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (row0 + e < args.rowsA) {
+                                        const double v = scale_pow2(crt_finish<SPLIT>(N, s1[4 * cc + e], s2[4 * cc + e]), sa[e] + sb);
+                                        cptr[e] = combine<T>(args.ab_mode, alpha, beta, cast_out<T>(v), cptr + e);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(crt_empty_bar);
+            }
         }
     }
 
@@ -379,12 +486,17 @@ bool make_operand_map(CUtensorMap *map, const int8_t *base, size_t ld8i, size_t 
     return r == CUDA_SUCCESS;
 }
 
-KernelArgs make_args(const GemmProblem &p) {
+KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     KernelArgs a{};
     a.rowsA = (uint32_t)p.rowsA; a.rowsB = (uint32_t)p.rowsB;
     a.num_kb = (uint32_t)((p.ld8i + BLOCK_K - 1) / BLOCK_K);
     a.first_modulus = p.first_modulus;
-    a.sched.init((uint32_t)((p.rowsA + BLOCK_M - 1) / BLOCK_M), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N), p.num_slices);
+    a.num_slices = p.num_slices;
+    a.tile_major = tile_major ? 1u : 0u;
+    a.sched.init((uint32_t)((p.rowsA + BLOCK_M - 1) / BLOCK_M), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N),
+                 tile_major ? 1u : p.num_slices);
+    a.C = p.C; a.ldc = p.ldc; a.sftA = p.sftA; a.sftB = p.sftB; a.alpha = p.alpha; a.beta = p.beta;
+    a.ab_mode = alpha_beta_mode(p.alpha, p.beta);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
     a.C32i = p.C32i; a.ldc32i = p.ldc32i;
     a.rowmax = p.rowmax; a.colmax = p.colmax;
@@ -401,13 +513,15 @@ int sm_count() {
     return n;
 }
 
-template <int EPI>
+template <int EPI, typename T = double, bool SPLIT = false>
 cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, BLOCK_M)) return cudaErrorInvalidValue;
     if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, BLOCK_N)) return cudaErrorInvalidValue;
-    KernelArgs a = make_args(p);
-    auto kern = oz_gemm_tcgen05_kernel<EPI>;
+    const char *dbg = getenv("OZ_DEBUG_SCHED");   // tuning knob: "tile" forces the tile-major schedule, "skipcrt" idles the CRT warps
+    KernelArgs a = make_args(p, EPI == EPI_CRT || (dbg && strstr(dbg, "tile")));
+    a.debug_skip_crt = (dbg && strstr(dbg, "skipcrt")) ? 1 : 0;
+    auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
@@ -433,6 +547,9 @@ cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStre
         case EPI_RESIDUE: return launch_tc<EPI_RESIDUE>(p, st);
         case EPI_INT32:   return launch_tc<EPI_INT32>(p, st);
         case EPI_ABSMAX:  return launch_tc<EPI_ABSMAX>(p, st);
+        case EPI_CRT:
+            if (p.dtype_C == DT_F32) return launch_tc<EPI_CRT, float, false>(p, st);
+            return p.split_weights ? launch_tc<EPI_CRT, double, true>(p, st) : launch_tc<EPI_CRT, double, false>(p, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -443,6 +560,7 @@ cudaError_t launch_gemm_simt(const GemmProblem &p, GemmEpilogue epi, cudaStream_
         case EPI_RESIDUE: return launch_simt_t<EPI_RESIDUE>(p, st);
         case EPI_INT32:   return launch_simt_t<EPI_INT32>(p, st);
         case EPI_ABSMAX:  return launch_simt_t<EPI_ABSMAX>(p, st);
+        case EPI_CRT:     return cudaErrorInvalidValue;  // the cross-check path runs EPI_RESIDUE + the stand-alone CRT kernel
     }
     return cudaErrorInvalidValue;
 }

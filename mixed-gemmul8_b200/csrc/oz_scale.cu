@@ -118,65 +118,83 @@ __global__ void __launch_bounds__(W) fast_shift_contig_kernel(const T *__restric
 
 // ---------------------------------------------------------------------------------------------
 // fast-mode shifts, strided vectors (rows of a column-major matrix): 32 vectors per CTA, lane ==
-// vector, 16 warps.  Warp w owns the virtual threads [w*W/16, (w+1)*W/16) of every vector, i.e.
-// element i goes to accumulator (i mod W) and is added in increasing i -- the reference's order.
+// vector (every warp load is one contiguous 32-element segment), W/32 warps.  Warp g plays the
+// reference's warp g: its lanes' 32 virtual threads [32g, 32g+32) live in 32 registers of ONE
+// thread, element i goes to accumulator (i mod W) in increasing i -- the reference's order -- and
+// the reference's shuffle tree becomes register arithmetic (only the operands that reach lane 1
+// are evaluated: lanes 1..31, lane 16 twice -- see the note at the top of this file).
 // ---------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ R ref_tree_lane1(const R (&v)[32]) {
+    R a[17], b[9];
+#pragma unroll
+    for (int i = 1; i <= 16; ++i) a[i] = add_ru(v[i], (i + 16 < 32) ? v[i + 16] : v[i]);   // o = 16, lanes 1..16
+#pragma unroll
+    for (int i = 1; i <= 8; ++i) b[i] = add_ru(a[i], a[i + 8]);                            // o = 8,  lanes 1..8
+#pragma unroll
+    for (int i = 1; i <= 4; ++i) a[i] = add_ru(b[i], b[i + 4]);                            // o = 4,  lanes 1..4
+    b[1] = add_ru(a[1], a[3]);                                                              // o = 2,  lanes 1..2
+    b[2] = add_ru(a[2], a[4]);
+    return add_ru(b[1], b[2]);                                                              // o = 1,  lane 1
+}
+// second-level tree of the reference: NW warp values in lanes 0..NW-1, zeros above, lane 0 kept
+template <typename R, int NW> __device__ __forceinline__ R ref_tree_lane0(const R *u, int stride) {
+    R v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (i < NW) ? u[i * stride] : R(0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < o; ++i) v[i] = add_ru(v[i], v[i + o]);   // lanes >= o no longer feed lane 0
+    }
+    return v[0];
+}
+
 template <typename T, int W>
-__global__ void __launch_bounds__(512) fast_shift_strided_kernel(const T *__restrict__ X, size_t ld, size_t nvec,
-                                                                 size_t len, float log2M, int16_t *__restrict__ out) {
+__global__ void __launch_bounds__(W) fast_shift_strided_kernel(const T *__restrict__ X, size_t ld, size_t nvec,
+                                                               size_t len, float log2M, int16_t *__restrict__ out) {
     using R = typename Real<T>::type;
-    constexpr int Q  = W / 16;   // virtual threads per warp
-    constexpr int NW = W / 32;   // reference warps per vector
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    R *s_part = reinterpret_cast<R *>(smem_raw);  // [W][33]   partial sums, [virtual thread][vector]
-    R *s_amax = s_part + W * 33;                  // [16][32]
-    R *s_u    = s_amax + 16 * 32;                 // [32][NW]  per reference-warp values
+    constexpr int NW = W / 32;
+    __shared__ R s_u[NW][33];
+    __shared__ R s_amax[NW][33];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t vec  = (size_t)blockIdx.x * 32 + lane;
     const bool active = vec < nvec;
     const T *__restrict__ p = X + (active ? vec : 0);
 
-    R acc[Q];
+    R acc[32];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) acc[q] = 0;
+    for (int q = 0; q < 32; ++q) acc[q] = 0;
     R amax = 0;
     if (active) {
-        constexpr int CH = Q < 8 ? Q : 8;  // loads in flight per lane
-        for (size_t base = (size_t)warp * Q; base < len; base += W) {
+        size_t base = (size_t)warp * 32;
+        for (; base + 32 <= len; base += W) {
+            const T *__restrict__ pb = p + base * ld;
+            constexpr int CH = sizeof(T) <= 8 ? 32 : 16;   // loads in flight per lane
 #pragma unroll
-            for (int q0 = 0; q0 < Q; q0 += CH) {
+            for (int q0 = 0; q0 < 32; q0 += CH) {
                 T x[CH];
 #pragma unroll
-                for (int q = 0; q < CH; ++q)
-                    if (base + q0 + q < len) x[q] = p[(base + q0 + q) * ld];
+                for (int q = 0; q < CH; ++q) x[q] = pb[(size_t)(q0 + q) * ld];
 #pragma unroll
-                for (int q = 0; q < CH; ++q)
-                    if (base + q0 + q < len) accumulate<T, R>(x[q], amax, acc[q0 + q]);
+                for (int q = 0; q < CH; ++q) accumulate<T, R>(x[q], amax, acc[q0 + q]);
             }
         }
-    }
+        if (base < len) {
 #pragma unroll
-    for (int q = 0; q < Q; ++q) s_part[(warp * Q + q) * 33 + lane] = acc[q];
-    s_amax[warp * 32 + lane] = amax;
-    __syncthreads();
-
-    // level 1: for every (vector r, reference warp g) run the reference's tree on the 32 partials
-    for (int t = warp; t < 32 * NW; t += 16) {
-        const int r = t & 31, g = t >> 5;
-        R v = s_part[(g * 32 + lane) * 33 + r];
-        v   = tree_sum_ru(v);
-        if (lane == 1) s_u[r * NW + g] = v;
+            for (int q = 0; q < 32; ++q)
+                if (base + q < len) accumulate<T, R>(p[(base + q) * ld], amax, acc[q]);
+        }
     }
+    s_u[warp][lane]    = ref_tree_lane1(acc);
+    s_amax[warp][lane] = amax;
     __syncthreads();
-    // level 2 + shift
-    for (int r = warp; r < 32; r += 16) {
-        R s = (lane < NW) ? s_u[r * NW + lane] : R(0);
-        s   = tree_sum_ru(s);
-        R a = (lane < 16) ? s_amax[lane * 32 + r] : R(0);
-        a   = tree_max(a);
-        const size_t v = (size_t)blockIdx.x * 32 + r;
-        if (lane == 0 && v < nvec) out[v] = (int16_t)(-fast_sft(a, s, log2M));
+    if (warp == 0 && active) {
+        R a = 0;
+#pragma unroll
+        for (int g = 0; g < NW; ++g) a = fmax(a, s_amax[g][lane]);
+        const R s = ref_tree_lane0<R, NW>(&s_u[0][lane], 33);
+        out[vec] = (int16_t)(-fast_sft(a, s, log2M));
     }
 }
 
@@ -187,15 +205,21 @@ __global__ void __launch_bounds__(512) fast_shift_strided_kernel(const T *__rest
 struct ModConst {
     double neg_m, rcp;
     float neg_mf, rcpf;
+    int m, half, neg_mi;
 };
 __device__ __forceinline__ ModConst load_mod(unsigned j) {
     ModConst c;
-    c.neg_m  = -(double)OZ_MOD[j];
+    c.m      = OZ_MOD[j];
+    c.half   = c.m >> 1;
+    c.neg_mi = -c.m;
+    // int -> fp through the exponent trick (exact; keeps I2F off the conversion pipe)
+    c.neg_m  = 4503599627370496.0 - __hiloint2double(0x43300000, c.m);
     c.rcp    = OZ_RCP64[j];
-    c.neg_mf = -(float)OZ_MOD[j];
+    c.neg_mf = 8388608.0f - __int_as_float(0x4B000000 | c.m);
     c.rcpf   = OZ_RCP32[j];
     return c;
 }
+// The reference's operation sequence, instruction for instruction (any magnitude).
 __device__ __forceinline__ int residue(double a, const ModConst &c) {
     float t = __double2float_rn(fma(rint(__dmul_rn(a, c.rcp)), c.neg_m, a));
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
@@ -209,11 +233,66 @@ __device__ __forceinline__ int residue(float a, const ModConst &c) {
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
     return __float2int_rz(t);
 }
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+// Same low byte for |a| below SmallLimit with ONE fp instruction per (element, modulus) and no
+// conversion-pipe work (FRND / F2F / F2I issue at a quarter of the FP64 rate on sm_100 and bound
+// the reference's sequence).  Why the result is identical:
+//   * the reference ends on the symmetric residue of a mod m: its first remainder t = a - q*m is
+//     an exact integer, and the float passes that follow subtract / add m until |t| <= m/2 (t/m is
+//     a multiple of 1/m, so rintf can only tie for m = 256, where +-128 both wrap to int8 -128);
+//   * so ANY quotient q with |a - q*m| <= 1.5 m followed by "fold once towards zero from either
+//     side" lands on the same byte.  Here q = rint(a * rcp) comes out of the low word of
+//     fma(a, rcp, 1.5*2^52) (|a * rcp| < 2^51; |a/m - q| <= 0.5 + 2^-53 |a/m| < 0.6), and
+//     t = a - q*m is evaluated modulo 2^32 on the low words (|t| < 2^9, so nothing is lost).
+template <typename R> struct SmallLimit;
+template <> struct SmallLimit<double> { static constexpr double value = 0x1p57; };
+template <> struct SmallLimit<float> { static constexpr float value = 0x1p24f; };
+__device__ __forceinline__ int fold_once(int ti, int half, int m) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.gt.s32 p, %0, %1;\n\t"
+        "@p sub.s32 %0, %0, %2;\n\t"
+        "setp.lt.s32 q, %0, %3;\n\t"
+        "@q add.s32 %0, %0, %2;\n\t}"
+        : "+r"(ti)
+        : "r"(half), "r"(m), "r"(-half));
+    return ti;
 }
-__device__ __forceinline__ double scale_trunc(double x, int sft) { return trunc(scalbn(x, sft)); }
-__device__ __forceinline__ float scale_trunc(float x, int sft) { return truncf(scalbnf(x, sft)); }
+// low 32 bits of the (exactly integer) value a, two's complement
+__device__ __forceinline__ int low_word(double a) { return (int)__double2ll_rz(a); }
+__device__ __forceinline__ int low_word(float a) { return __float2int_rz(a); }
+__device__ __forceinline__ int residue_small(double a, int a_lo, const ModConst &c) {
+    const int q = __double2loint(fma(a, c.rcp, 6755399441055744.0));  // 1.5 * 2^52
+    return fold_once(q * c.neg_mi + a_lo, c.half, c.m);
+}
+__device__ __forceinline__ int residue_small(float a, int a_lo, const ModConst &c) {
+    const int q = __float_as_int(__fmaf_rn(a, c.rcpf, 12582912.0f)) - 0x4B400000;  // 1.5 * 2^23
+    return fold_once(q * c.neg_mi + a_lo, c.half, c.m);
+}
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {  // low bytes, 3 PRMT
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+// trunc(x * 2^sft): scalbn by an exact power-of-two product.  One factor when 2^sft is a normal
+// number, two otherwise (tiny operands); a result too small to be normal truncates to 0 either way.
+template <typename R> struct Pow2 {
+    R f1, f2;
+    bool two;
+    __device__ __forceinline__ explicit Pow2(int sft) {
+        constexpr int lim = sizeof(R) == 8 ? 1022 : 126;
+        two = sft > lim || sft < -lim;
+        const int s1 = two ? sft / 2 : sft, s2 = sft - s1;
+        if constexpr (sizeof(R) == 8) {
+            f1 = __hiloint2double((1023 + s1) << 20, 0);
+            f2 = __hiloint2double((1023 + s2) << 20, 0);
+        } else {
+            f1 = __int_as_float((127 + s1) << 23);
+            f2 = __int_as_float((127 + s2) << 23);
+        }
+    }
+    __device__ __forceinline__ R operator()(R x) const {
+        R y = x * f1;
+        if (two) y *= f2;
+        if constexpr (sizeof(R) == 8) return trunc(y); else return truncf(y);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // encode, contiguous vectors.  One thread = 4 consecutive k of one vector (the LSU sweet spot:
@@ -228,7 +307,7 @@ __global__ void __launch_bounds__(256) encode_contig_kernel(const R *__restrict_
     const size_t g   = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 along k
     const size_t i0  = g * 4;
     if (i0 >= ld8i) return;
-    const int sft = -(int)sft_neg[vec];
+    const Pow2<R> scale(-(int)sft_neg[vec]);
     const R *__restrict__ p = X + vec * ld;
     R v[4];
     if (i0 + 3 < len && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
@@ -244,13 +323,26 @@ __global__ void __launch_bounds__(256) encode_contig_kernel(const R *__restrict_
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = (i0 + e < len) ? p[i0 + e] : R(0);
     }
+    bool small = true;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = scale_trunc(v[e], sft);
+    for (int e = 0; e < 4; ++e) { v[e] = scale(v[e]); small &= fabs(v[e]) < SmallLimit<R>::value; }
     int8_t *__restrict__ o = out + vec * ld8i + i0;
-    for (unsigned j = 0; j < num_moduli; ++j) {
-        const ModConst c = load_mod(j);
-        *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) =
-            pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
+    if (small) {
+        int lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lo[e] = low_word(v[e]);
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) =
+                pack4(residue_small(v[0], lo[0], c), residue_small(v[1], lo[1], c), residue_small(v[2], lo[2], c),
+                      residue_small(v[3], lo[3], c));
+        }
+    } else {
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) =
+                pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
+        }
     }
 }
 
@@ -272,13 +364,13 @@ __global__ void __launch_bounds__(256) encode_strided_kernel(const R *__restrict
     {
         const size_t vec = v0 + lane;
         const bool active = vec < nvec;
-        const int sft = active ? -(int)sft_neg[vec] : 0;
+        const Pow2<R> scale(active ? -(int)sft_neg[vec] : 0);
         const R *__restrict__ p = X + (active ? vec : 0);
-#pragma unroll 4
+#pragma unroll 8
         for (int kk = warp; kk < 128; kk += 8) {
             const size_t k = k0 + kk;
             R x = (active && k < len) ? p[k * ld] : R(0);
-            tile[kk * 32 + ((lane + 4 * (kk >> 4)) & 31)] = scale_trunc(x, sft);
+            tile[kk * 32 + ((lane + 4 * (kk >> 4)) & 31)] = scale(x);
         }
     }
     __syncthreads();
@@ -287,17 +379,36 @@ __global__ void __launch_bounds__(256) encode_strided_kernel(const R *__restrict
     const size_t kb  = k0 + 16 * g;
     if (vec >= nvec || kb >= ld8i) return;
     R v[16];
+    bool small = true;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = tile[(16 * g + e) * 32 + ((r + 4 * g) & 31)];
+    for (int e = 0; e < 16; ++e) {
+        v[e] = tile[(16 * g + e) * 32 + ((r + 4 * g) & 31)];
+        small &= fabs(v[e]) < SmallLimit<R>::value;
+    }
     int8_t *__restrict__ o = out + vec * ld8i + kb;
-    for (unsigned j = 0; j < num_moduli; ++j) {
-        const ModConst c = load_mod(j);
-        uint4 w;
-        w.x = pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
-        w.y = pack4(residue(v[4], c), residue(v[5], c), residue(v[6], c), residue(v[7], c));
-        w.z = pack4(residue(v[8], c), residue(v[9], c), residue(v[10], c), residue(v[11], c));
-        w.w = pack4(residue(v[12], c), residue(v[13], c), residue(v[14], c), residue(v[15], c));
-        *reinterpret_cast<uint4 *>(o + (size_t)j * inc) = w;  // ld8i % 16 == 0 and kb % 16 == 0
+    if (small) {
+        int lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) lo[e] = low_word(v[e]);
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                w[e] = pack4(residue_small(v[4 * e], lo[4 * e], c), residue_small(v[4 * e + 1], lo[4 * e + 1], c),
+                             residue_small(v[4 * e + 2], lo[4 * e + 2], c), residue_small(v[4 * e + 3], lo[4 * e + 3], c));
+            *reinterpret_cast<uint4 *>(o + (size_t)j * inc) = make_uint4(w[0], w[1], w[2], w[3]);  // ld8i % 16 == 0 and kb % 16 == 0
+        }
+    } else {
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            uint4 w;
+            w.x = pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
+            w.y = pack4(residue(v[4], c), residue(v[5], c), residue(v[6], c), residue(v[7], c));
+            w.z = pack4(residue(v[8], c), residue(v[9], c), residue(v[10], c), residue(v[11], c));
+            w.w = pack4(residue(v[12], c), residue(v[13], c), residue(v[14], c), residue(v[15], c));
+            *reinterpret_cast<uint4 *>(o + (size_t)j * inc) = w;
+        }
     }
 }
 
@@ -402,13 +513,7 @@ cudaError_t run_fast_shifts(bool strided, const void *X, size_t ld, size_t nvec,
     using R = typename Real<T>::type;
     if (nvec == 0) return cudaSuccess;
     if (strided) {
-        const size_t smem = sizeof(R) * (W * 33 + 16 * 32 + 32 * (W / 32));
-        auto kern = fast_shift_strided_kernel<T, W>;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        kern<<<(unsigned)((nvec + 31) / 32), 512, smem, st>>>(static_cast<const T *>(X), ld, nvec, len, log2M, out);
+        fast_shift_strided_kernel<T, W><<<(unsigned)((nvec + 31) / 32), W, 0, st>>>(static_cast<const T *>(X), ld, nvec, len, log2M, out);
     } else {
         fast_shift_contig_kernel<T, W><<<(unsigned)nvec, W, 0, st>>>(static_cast<const T *>(X), ld, len, log2M, out);
     }

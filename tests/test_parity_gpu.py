@@ -172,6 +172,24 @@ def test_tcgen05_gemm_equals_cuda_core_gemm(g):
         assert torch.equal(out[:, :m].to(torch.int64), want)
 
 
+@pytest.mark.parametrize("m,n,k,N,dt,alpha,beta", [
+    (777, 1301, 900, 14, "float64", 1.0, 0.0),      # ragged tiles, split weights
+    (300, 515, 256, 7, "float64", 0.5, 2.0),        # single weights, general alpha/beta
+    (129, 257, 130, 6, "float32", 1.0, 1.0),        # fp32 output
+    (2048, 4096, 512, 20, "float64", 1.0, 0.0),     # more tiles than SMs x 1, 20 moduli
+])
+def test_fused_crt_equals_unfused(g, m, n, k, N, dt, alpha, beta):
+    """The single-kernel variant (CRT warps behind the last modulus, tile-major schedule; FLAG_FUSED_CRT)
+    against the default residues-to-HBM + stand-alone CRT kernel (item-major schedule): bit-identical."""
+    torch = torch_()
+    A, B = operands(g, m, n, k, 0, 0, getattr(torch, dt), getattr(torch, dt), seedB=77)
+    C0 = g.phi_matrix(m, n, 1.0, getattr(torch, dt), seed=5)
+    C_f, v_f = run_ours(g, m, n, k, N, True, A, B, alpha=alpha, beta=beta, C0=C0, flags=g.FLAG_FUSED_CRT)
+    C_u, v_u = run_ours(g, m, n, k, N, True, A, B, alpha=alpha, beta=beta, C0=C0)
+    assert torch.equal(v_f["C8u"][:, :, :m], v_u["C8u"][:, :, :m])
+    assert torch.equal(C_f, C_u)
+
+
 def test_leading_dimensions_and_determinism(g):
     torch = torch_()
     m, n, k, N = 333, 222, 444, 14

@@ -1,0 +1,38 @@
+"""Time the GEMM-phase variants on ONE box (clocks differ between boxes): prints ms per phase."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gemmul8_b200 as g
+
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 14
+m = n = k = S
+A = g.phi_matrix(m, k, 0.5, torch.float64)
+B = g.phi_matrix(k, n, 0.5, torch.float64)
+work = torch.empty(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+C = torch.zeros((n, m), dtype=torch.float64, device="cuda")
+
+def run(name, flags, env):
+    if env is None:
+        os.environ.pop("OZ_DEBUG_SCHED", None)
+    else:
+        os.environ["OZ_DEBUG_SCHED"] = env
+    for _ in range(3):
+        g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=flags)
+    torch.cuda.synchronize()
+    ph = [0.0] * 4
+    reps = 8
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        t = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=flags | g.FLAG_TIMERS)
+        ph = [a + b for a, b in zip(ph, t)]
+    e1.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"variant": name, "total_ms": e0.elapsed_time(e1) / reps, "phases_ms": [p / reps / 1e6 for p in ph]}), flush=True)
+
+for rep in range(2):
+    run("default (item-major + crt kernel)", 0, None)
+    run("unfused tile-major", 0, "tile")
+    run("fused", g.FLAG_FUSED_CRT, None)
+    run("fused skipcrt", g.FLAG_FUSED_CRT, "skipcrt")
