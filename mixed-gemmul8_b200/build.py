@@ -40,13 +40,13 @@ def _run(cmd):
 
 
 def build(force=False, verbose=False):
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gemmul8_b200.h")]
-    core = [os.path.join(CSRC, f) for f in ("oz_api.cu", "oz_scale.cu", "oz_gemm.cu", "oz_crt.cu", "oz_complex.cu")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gemmul8_b200.h"), os.path.join(HERE, "..", "include", "gemmul8.hpp")]
+    core = [os.path.join(CSRC, f) for f in ("oz_api.cu", "oz_scale.cu", "oz_gemm.cu", "oz_crt.cu", "oz_complex.cu", "oz_cxx_api.cu")
             if os.path.exists(os.path.join(CSRC, f))]
     out = ""
     if force or _stale(LIB, deps):
         extra = ["-Xptxas", "-v"] if verbose else []
-        out += _run([nvcc(), *ARCH, *COMMON, *extra, "-shared", "-o", LIB, *core])
+        out += _run([nvcc(), *ARCH, *COMMON, *extra, "-shared", "-o", LIB, *core, "-ldl"])
     aux_src = os.path.join(CSRC, "oz_aux.cu")
     if os.path.exists(aux_src) and (force or _stale(AUX, [aux_src])):
         out += _run([nvcc(), *ARCH, *COMMON, "-shared", "-o", AUX, aux_src, "-lcublas"])
