@@ -213,6 +213,34 @@ def work_views(work, L, num_moduli, m, n):
     return v
 
 
+def work_views_complex(work, L, num_moduli, m, n, k, computeType):
+    """Typed views of `work` for complex calls, as the reference carves it
+    (big matrix: GEMMul8/src/gemmul8.cu:659-664; CLASSIC / KARATSUBA: :806-815).
+    big matrix : A8i (N, m2_pad, lda8i) with rows [Pr | -Pi] then [Pi | Pr]; B8i (N, n, lda8i) = [Qr | Qi];
+                 C8u (N, n, m2_pad) with Re in rows < m and Im in rows m .. 2m-1
+    otherwise  : A8i_real / A8i_imag, B8i_real / B8i_imag, C8u_real / C8u_imag"""
+    import torch
+    N = num_moduli
+    v = {}
+
+    def stack8(off, rows):
+        return work[off:off + N * rows * L.lda8i].view(torch.int8).view(N, rows, L.lda8i)
+
+    def stackC(off):
+        return work[off:off + N * L.sizeC].view(N, L.sizeC)[:, :L.m_pad * n].view(N, n, L.m_pad)
+
+    if computeType == COMPLEX_BIG_MATRIX_ENCODE:
+        v["A8i"], v["B8i"], v["C8u"] = stack8(L.off_A8i, L.m_pad), stack8(L.off_B8i, n), stackC(L.off_C8u)
+        v["C8u_real"], v["C8u_imag"] = v["C8u"][:, :, :m], v["C8u"][:, :, m:2 * m]
+    else:
+        v["A8i_real"], v["A8i_imag"] = stack8(L.off_A8i, L.m_pad), stack8(L.off_A8i_imag, L.m_pad)
+        v["B8i_real"], v["B8i_imag"] = stack8(L.off_B8i, n), stack8(L.off_B8i_imag, n)
+        v["C8u_real"], v["C8u_imag"] = stackC(L.off_C8u)[:, :, :m], stackC(L.off_C8u_imag)[:, :, :m]
+    v["sftA"] = work[L.off_sftA:L.off_sftA + 2 * m].view(torch.int16)
+    v["sftB"] = work[L.off_sftB:L.off_sftB + 2 * n].view(torch.int16)
+    return v
+
+
 def launch_count():
     """Kernels launched by the library so far (process-wide)."""
     return lib().gemmul8_b200_launch_count()

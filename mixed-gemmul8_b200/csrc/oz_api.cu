@@ -206,6 +206,109 @@ int gemm_real(gemmul8_b200_args *a) {
     return GEMMUL8_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// complex types: reference gemm_mixed_bigmatrix / gemm_mixed_kara / gemm_mixed_classic,
+// GEMMul8/src/gemmul8.cu:579-1052 (dispatch :1146-1178)
+// ---------------------------------------------------------------------------------------------
+int gemm_complex(gemmul8_b200_args *a) {
+    const size_t m = a->m, n = a->n, k = a->k;
+    const unsigned N = a->num_moduli, ti = N - 2;
+    const int ct = a->compute_type;
+    const bool big = ct == GEMMUL8_COMPLEX_BIG_MATRIX_ENCODE;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    oz::Layout L;
+    compute_layout(m, n, k, N, ct, L);
+    uint8_t *work    = static_cast<uint8_t *>(a->work);
+    int8_t *A_re     = reinterpret_cast<int8_t *>(work + L.off_A8i);
+    int8_t *A_im     = reinterpret_cast<int8_t *>(work + L.off_A8i_imag);
+    int8_t *B_re     = reinterpret_cast<int8_t *>(work + L.off_B8i);
+    int8_t *B_im     = reinterpret_cast<int8_t *>(work + L.off_B8i_imag);
+    uint8_t *C_re    = work + L.off_C8u;
+    uint8_t *C_im    = big ? C_re + m : work + L.off_C8u_imag;   // big matrix: Im rows follow the m Re rows
+    int16_t *sftA    = reinterpret_cast<int16_t *>(work + L.off_sftA);
+    int16_t *sftB    = reinterpret_cast<int16_t *>(work + L.off_sftB);
+
+    const bool a_strided = a->op_A == GEMMUL8_OP_N, b_strided = a->op_B != GEMMUL8_OP_N;
+    const bool a_conj = a->op_A == GEMMUL8_OP_C, b_conj = a->op_B == GEMMUL8_OP_C;
+    const bool simt = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) != 0;
+    auto gemm = simt ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
+
+    oz::ComplexTarget tA{}, tB{};
+    tA.layout = big ? 1 : 0; tA.out_re = A_re; tA.out_im = big ? nullptr : A_im; tA.ld8i = L.lda8i; tA.inc = L.sizeA; tA.k = k; tA.nvec = m;
+    tB.layout = big ? 2 : 0; tB.out_re = B_re; tB.out_im = big ? nullptr : B_im; tB.ld8i = L.lda8i; tB.inc = L.sizeB; tB.k = k; tB.nvec = n;
+    const size_t rowsA = big ? 2 * m : m;   // rows of the int8 A operand
+
+    PhaseTimer timer((a->flags & GEMMUL8_FLAG_TIMERS) != 0, st);
+    timer.mark();
+
+    // ---------------- phase 0: scaling ----------------
+    if (a->fastmode) {
+        const float l2 = oz::host_tab::OZ_LOG2M_FAST[ti];
+        OZ_CUDA(oz::launch_fast_shifts(a->dtype_A, a_strided, a->A, a->lda, m, k, 128, l2, sftA, st), "fast shifts A");
+        OZ_CUDA(oz::launch_fast_shifts(a->dtype_B, b_strided, a->B, a->ldb, n, k, 128, l2, sftB, st), "fast shifts B");
+    } else {
+        // reference: int8tc::scaling_bigmatrix / scaling_kara, GEMMul8/src/scaling.hpp:3138-3367.
+        // Whatever the compute type, the bound product is Re = |Pr||Qr| -+ |Pi||Qi|, Im = |Pi||Qr| +- |Pr||Qi|;
+        // in the big-matrix layout that is ONE int8 product, and only its row / column maxima are needed.
+        // CLASSIC / KARATSUBA borrow the (still empty) A / B slice stacks for the temporary big bound
+        // matrices: ceil16(2k) * ceil4(2m) <= 4 sizeA <= 2 N sizeA.
+        const size_t ld_big = ceil_to(2 * k, 16);
+        oz::ComplexTarget bA = tA, bB = tB;
+        bA.layout = 1; bA.out_im = nullptr; bA.ld8i = ld_big;
+        bB.layout = 2; bB.out_im = nullptr; bB.ld8i = ld_big;
+        OZ_CUDA(oz::launch_bound_extract_complex(a->dtype_A, a_strided, a->A, a->lda, m, k, sftA, bA, a_conj, st), "bound extract A");
+        OZ_CUDA(oz::launch_bound_extract_complex(a->dtype_B, b_strided, a->B, a->ldb, n, k, sftB, bB, b_conj, st), "bound extract B");
+        // maxima: 2m + n int32 at the start of the residue area ((N+4) sizeC >= 12 m n bytes: always enough)
+        int32_t *rowmax = reinterpret_cast<int32_t *>(C_re);
+        int32_t *colmax = rowmax + 2 * m;
+        OZ_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(int32_t) * (2 * m + n), st), "memset maxima");
+        oz::GemmProblem bp{};
+        bp.A8i = A_re; bp.B8i = B_re; bp.rowsA = 2 * m; bp.rowsB = n; bp.ld8i = ld_big;
+        bp.sizeA = ld_big * ceil_to(2 * m, 4); bp.sizeB = ld_big * n; bp.num_slices = 1; bp.first_modulus = 0;
+        bp.rowmax = rowmax; bp.colmax = colmax;
+        OZ_CUDA(gemm(bp, oz::EPI_ABSMAX, st), "bound product");
+        const float l2 = oz::host_tab::OZ_LOG2M_ACC[ti];
+        OZ_CUDA(oz::launch_accurate_shifts(m, rowmax, l2, sftA, st, m), "accurate shifts A");   // Re row r and Im row r + m
+        OZ_CUDA(oz::launch_accurate_shifts(n, colmax, l2, sftB, st), "accurate shifts B");
+    }
+    OZ_CUDA(oz::launch_encode_complex(a->dtype_A, a_strided, a->A, a->lda, m, k, sftA, N, tA, a_conj, st), "encode A");
+    OZ_CUDA(oz::launch_encode_complex(a->dtype_B, b_strided, a->B, a->ldb, n, k, sftB, N, tB, b_conj, st), "encode B");
+    timer.mark();
+    if (a->flags & GEMMUL8_FLAG_STAGE_SCALING) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
+
+    // ---------------- phases 1+2: products mod m_j ----------------
+    oz::GemmProblem gp{};
+    gp.rowsA = rowsA; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
+    gp.num_slices = N; gp.first_modulus = 0; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    auto product = [&](const int8_t *A8, const int8_t *B8, uint8_t *C8, int combine, uint8_t *aux) -> cudaError_t {
+        gp.A8i = A8; gp.B8i = B8; gp.C8u = C8; gp.combine = combine; gp.C8u_aux = aux;
+        return gemm(gp, oz::EPI_RESIDUE, st);
+    };
+    if (big) {
+        OZ_CUDA(product(A_re, B_re, C_re, oz::RC_STORE, nullptr), "big-matrix product");
+    } else if (ct == GEMMUL8_COMPLEX_CLASSIC_MULT) {
+        OZ_CUDA(product(A_re, B_re, C_re, oz::RC_STORE, nullptr), "Ar Br");
+        OZ_CUDA(product(A_im, B_im, C_re, oz::RC_SUB, nullptr), "Ai Bi");
+        OZ_CUDA(product(A_im, B_re, C_im, oz::RC_STORE, nullptr), "Ai Br");
+        OZ_CUDA(product(A_re, B_im, C_im, oz::RC_ADD, nullptr), "Ar Bi");
+    } else {  // Karatsuba: E = ArBr, F = AiBi, G = (Ar+Ai)(Br+Bi); Re = E - F, Im = G - (E + F)
+        OZ_CUDA(product(A_re, B_re, C_re, oz::RC_STORE, nullptr), "E");
+        OZ_CUDA(product(A_im, B_im, C_re, oz::RC_KARATSUBA_F, C_im), "F");
+        OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeA, A_re, A_im, st), "Ar + Ai");   // in place, as the reference (gemmul8.cu:853-855)
+        OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeB, B_re, B_im, st), "Br + Bi");
+        OZ_CUDA(product(A_re, B_re, C_im, oz::RC_RSUB, nullptr), "G");
+    }
+    timer.mark();
+    if (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
+
+    // ---------------- phase 3: CRT + inverse scaling ----------------
+    const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_C64;
+    OZ_CUDA(oz::launch_crt_complex(a->dtype_C, split, N, m, n, C_re, C_im, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, st), "crt");
+    timer.mark();
+    timer.finish(a->timers_ns);
+    return GEMMUL8_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -236,7 +339,10 @@ int gemmul8_b200_gemm(gemmul8_b200_args *a) {
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
         return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
-    if (is_complex(a->dtype_C)) return fail(GEMMUL8_ERR_ARGUMENT, "complex types: not implemented yet in this build");
+    if (is_complex(a->dtype_C)) {
+        if (a->k > (size_t(1) << 16)) return fail(GEMMUL8_ERR_ARGUMENT, "complex types: k must be <= 2^16 (int32 accumulation)");
+        return gemm_complex(a);
+    }
     return gemm_real(a);
 }
 

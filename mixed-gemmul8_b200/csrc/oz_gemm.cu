@@ -159,6 +159,7 @@ struct KernelArgs {
     uint32_t tile_major, num_slices;
     Sched sched;
     uint8_t *C8u; size_t ldc8u, sizeC;
+    int combine; uint8_t *C8u_aux;
     int32_t *C32i; size_t ldc32i;
     int32_t *rowmax; int32_t *colmax;
     // EPI_CRT
@@ -189,6 +190,24 @@ __device__ __forceinline__ uint32_t reduce_mod(int32_t x, int32_t m, int32_t inv
     r -= (r >= m) ? m : 0;
     r += (r < 0) ? m : 0;
     return (uint32_t)r;
+}
+
+// r, stored residues in [0, m); see ResidueCombine.  Returns what goes to *out.
+__device__ __forceinline__ uint32_t combine_residue(int rc, uint32_t r, const uint8_t *out, uint8_t *aux, int32_t m) {
+    const int32_t old = (int32_t)*out, rn = (int32_t)r;
+    int32_t t;
+    if (rc == RC_ADD) t = old + rn;
+    else if (rc == RC_SUB) t = old - rn;
+    else if (rc == RC_RSUB) t = rn - old;
+    else {  // RC_KARATSUBA_F
+        int32_t u = old + rn;
+        u -= (u >= m) ? m : 0;
+        *aux = (uint8_t)u;
+        t = old - rn;
+    }
+    t -= (t >= m) ? m : 0;
+    t += (t < 0) ? m : 0;
+    return (uint32_t)t;
 }
 
 template <int EPI, typename T = double, bool SPLIT = false>
@@ -291,6 +310,8 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const int32_t m    = dev_tab::OZ_MOD[mj];
                 const int32_t inv  = (int32_t)(4294967296ull / (uint32_t)m);
                 uint8_t *out = args.C8u + (size_t)j * args.sizeC + row;  // (re-read below under EPI_CRT: no __restrict__)
+                uint8_t *aux = args.C8u_aux + (size_t)j * args.sizeC + row;
+                const int rc = args.combine;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 16) {
                     uint32_t v[16];
@@ -301,7 +322,8 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         for (int e = 0; e < 16; ++e) {
                             const uint32_t col = col0 + c + e;
                             if (col < args.rowsB) {
-                                const uint32_t r = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
+                                uint32_t r = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
+                                if (rc != RC_STORE) r = combine_residue(rc, r, out + (size_t)col * args.ldc8u, aux + (size_t)col * args.ldc8u, m);
                                 out[(size_t)col * args.ldc8u] = (uint8_t)r;
                             }
                         }
@@ -449,8 +471,11 @@ __global__ void oz_gemm_simt_kernel(const int8_t *__restrict__ A8i, const int8_t
         const uint32_t mj = args.first_modulus + j;
         const int32_t m   = dev_tab::OZ_MOD[mj];
         const int32_t inv = (int32_t)(4294967296ull / (uint32_t)m);
-        args.C8u[(size_t)j * args.sizeC + (size_t)col * args.ldc8u + row] =
-            (uint8_t)((mj == 0) ? ((uint32_t)acc & 0xffu) : reduce_mod(acc, m, inv));
+        uint8_t *out = args.C8u + (size_t)j * args.sizeC + (size_t)col * args.ldc8u + row;
+        uint8_t *aux = args.C8u_aux + (size_t)j * args.sizeC + (size_t)col * args.ldc8u + row;
+        uint32_t r   = (mj == 0) ? ((uint32_t)acc & 0xffu) : reduce_mod(acc, m, inv);
+        if (args.combine != RC_STORE) r = combine_residue(args.combine, r, out, aux, m);
+        *out = (uint8_t)r;
     } else if constexpr (EPI == EPI_INT32) {
         args.C32i[(size_t)col * args.ldc32i + row] = acc;
     } else {
@@ -498,6 +523,7 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     a.C = p.C; a.ldc = p.ldc; a.sftA = p.sftA; a.sftB = p.sftB; a.alpha = p.alpha; a.beta = p.beta;
     a.ab_mode = alpha_beta_mode(p.alpha, p.beta);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
+    a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
     a.C32i = p.C32i; a.ldc32i = p.ldc32i;
     a.rowmax = p.rowmax; a.colmax = p.colmax;
     return a;
