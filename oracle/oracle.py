@@ -131,6 +131,50 @@ def gemm_real(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, N, fa
     return r
 
 
+def gemm_complex(op_A, op_B, m, n, k, A, lda, B, ldb, Cmat, ldc, N, fastmode, ct):
+    """Whole complex path on the CPU (alpha = 1, beta = 0).  Returns reference-layout workspace views
+    (big matrix: A8i / B8i / C8u_real / C8u_imag; otherwise A8i_real, A8i_imag, ...)."""
+    ws = worksize(m, n, k, N, ct)
+    work = np.zeros(ws + 16, np.uint8)
+    amb_r = np.zeros(m, np.uint8)
+    amb_c = np.zeros(n, np.uint8)
+    rc = cpu().oracle_gemm_complex(C.c_int(op_A), C.c_int(op_B), C.c_size_t(m), C.c_size_t(n), C.c_size_t(k),
+                                   C.c_int(_NP_TAG[A.dtype]), _p(A), C.c_size_t(lda), C.c_int(_NP_TAG[B.dtype]), _p(B), C.c_size_t(ldb),
+                                   C.c_int(_NP_TAG[Cmat.dtype]), _p(Cmat), C.c_size_t(ldc), C.c_uint(N), C.c_int(int(fastmode)),
+                                   C.c_int(ct), _p(work), _p(amb_r), _p(amb_c))
+    if rc:
+        raise RuntimeError(f"oracle_gemm_complex failed ({rc})")
+    r = CpuResult()
+    big = ct == 1
+    ld8 = ((2 * k if big else k) + 15) // 16 * 16
+    m_pad = ((2 * m if big else m) + 3) // 4 * 4
+    sizeA, sizeB = ld8 * m_pad, ld8 * n
+    sizeC = (m_pad * n + 15) // 16 * 16
+    parts = 1 if big else 2
+    o = 0
+
+    def stack8(off, rows):
+        return work[off:off + N * rows * ld8].view(np.int8).reshape(N, rows, ld8)
+
+    def stackC(off):
+        return work[off:off + N * sizeC].reshape(N, sizeC)[:, :m_pad * n].reshape(N, n, m_pad)
+
+    if big:
+        r.A8i = stack8(0, m_pad); o = N * sizeA
+        r.B8i = stack8(o, n); o += N * sizeB
+        c = stackC(o); o += N * sizeC
+        r.C8u_real, r.C8u_imag = c[:, :, :m], c[:, :, m:2 * m]
+    else:
+        r.A8i_real, r.A8i_imag = stack8(0, m_pad), stack8(N * sizeA, m_pad); o = 2 * N * sizeA
+        r.B8i_real, r.B8i_imag = stack8(o, n), stack8(o + N * sizeB, n); o += 2 * N * sizeB
+        r.C8u_real, r.C8u_imag = stackC(o)[:, :, :m], stackC(o + N * sizeC)[:, :, :m]; o += 2 * N * sizeC
+    o += parts * 4 * sizeC
+    r.sftA = work[o:o + 2 * m].view(np.int16); o += 2 * ((m + 15) // 16 * 16)
+    r.sftB = work[o:o + 2 * n].view(np.int16)
+    r.amb_rows, r.amb_cols = amb_r, amb_c
+    return r
+
+
 def dd_gemm(m, n, k, A, lda, B, ldb):
     """Host double-double reference GEMM (restated eval::dd::simple_gemm); returns (C1, C2) as (n, m) arrays."""
     C1 = np.zeros((n, m), np.float64)
