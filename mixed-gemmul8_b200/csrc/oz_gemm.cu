@@ -11,8 +11,12 @@
 //   warp 1      MMA issuer  : tcgen05.mma.cta_group::1.kind::i8, M=128, N=256, K=32 per instruction,
 //                             accumulators double-buffered in TMEM (2 x 256 columns)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue    : tcgen05.ld (lane == row), Barrett reduction mod m_j, byte stores
-//   warps 8-11  CRT         : (EPI_CRT) once a tile's last modulus is stored, re-read its residues
+//   warps 4-7   epilogue    : tcgen05.ld (lane == row), Barrett reduction mod m_j, 32 x 16 byte transpose
+//                             through a padded smem scratch, then 4-byte stores (4 rows of one column);
+//                             complex passes first combine with the stored residue (ResidueCombine),
+//                             whose words were prefetched before the accumulator became ready
+//   warps 8-11  epilogue too (columns 128-255 of the tile; warps 4-7 then take columns 0-127), except under
+//               EPI_CRT    : once a tile's last modulus is stored, re-read its residues
 //                             column-wise (128-byte rows per load, 28 loads in flight per lane),
 //                             CRT + mod M + inverse scaling + alpha/beta, 1 KiB stores of C
 // A work item is (C tile, modulus).  Two schedules:
@@ -49,7 +53,8 @@ constexpr int SMEM_A  = BLOCK_M * BLOCK_K;
 constexpr int SMEM_B  = BLOCK_N * BLOCK_K;
 constexpr int SMEM_STAGE = SMEM_A + SMEM_B;
 constexpr int SMEM_BARRIERS = 256;
-constexpr int SMEM_TOTAL = STAGES * SMEM_STAGE + SMEM_BARRIERS + 1024;  // + slack for 1024-B alignment
+constexpr int SMEM_SCRATCH  = 8 * 32 * 5 * 4;  // per epilogue warp: 32 rows x 5 words (16 residue bytes + 1 pad word)
+constexpr int SMEM_TOTAL = STAGES * SMEM_STAGE + SMEM_BARRIERS + SMEM_SCRATCH + 1024;  // + slack for 1024-B alignment
 constexpr int BAND_M = 16;  // row tiles per scheduling band
 constexpr int NUM_THREADS = 384;
 constexpr uint32_t TMEM_COLS = 512;
@@ -210,7 +215,30 @@ __device__ __forceinline__ uint32_t combine_residue(int rc, uint32_t r, const ui
     return (uint32_t)t;
 }
 
-template <int EPI, typename T = double, bool SPLIT = false>
+// the same on four residues packed in a word (four rows of one column), two 16-bit lanes at a time:
+// values stay below 2^10, so plain 32-bit adds never carry between lanes
+__device__ __forceinline__ uint32_t fold_lanes(uint32_t t, uint32_t m, uint32_t k15) {   // lanes in [0, 2m) -> [0, m)
+    const uint32_t ge = ((t + k15) >> 15) & 0x00010001u;   // k15 = 0x8000 - m per lane: bit 15 <=> lane >= m
+    return t - ge * m;
+}
+__device__ __forceinline__ uint32_t combine_word(int rc, uint32_t rnew, uint32_t old, uint32_t &aux, int32_t mi) {
+    const uint32_t m = (uint32_t)mi, ml = m * 0x00010001u, k15 = (0x8000u - m) * 0x00010001u;
+    const uint32_t r0 = rnew & 0x00ff00ffu, r1 = (rnew >> 8) & 0x00ff00ffu;
+    const uint32_t o0 = old & 0x00ff00ffu, o1 = (old >> 8) & 0x00ff00ffu;
+    uint32_t t0, t1;
+    aux = 0;
+    if (rc == RC_ADD)       { t0 = o0 + r0;      t1 = o1 + r1; }
+    else if (rc == RC_SUB)  { t0 = o0 + ml - r0; t1 = o1 + ml - r1; }
+    else if (rc == RC_RSUB) { t0 = r0 + ml - o0; t1 = r1 + ml - o1; }
+    else {                  // RC_KARATSUBA_F: aux = old + new, out = old - new
+        aux = fold_lanes(o0 + r0, m, k15) | (fold_lanes(o1 + r1, m, k15) << 8);
+        t0 = o0 + ml - r0;  t1 = o1 + ml - r1;
+    }
+    // (a - b + m lies in [1, 2m - 1] and m - 0 = m folds to 0: one fold is enough everywhere)
+    return fold_lanes(t0, m, k15) | (fold_lanes(t1, m, k15) << 8);
+}
+
+template <int EPI, typename T = double, bool SPLIT = false, bool RMW = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const KernelArgs args) {
@@ -234,7 +262,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_CRT ? 128 : 256); }
         mbar_init(crt_full_bar, 128);
         mbar_init(crt_empty_bar, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -291,40 +319,78 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 tcgen05_commit(tfull_bar(acc));  // accumulator complete
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && (warp < 8 || EPI != EPI_CRT)) {
         // ===================== epilogue =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         uint32_t tm, tn, j;
+        // transposed store mapping: this lane stores rows 4*rg .. 4*rg+3 of columns 4*cg .. 4*cg+3 of a 16-column chunk
+        const int rg = lane & 7, cg = lane >> 3;
+        uint32_t *scr = reinterpret_cast<uint32_t *>(smem_raw + (bar_base + SMEM_BARRIERS - smem_u32(smem_raw))) + (warp - 4) * 160;
+        // column chunks (16 wide) of the tile this warp drains: all 16, or one half each for the two epilogue groups
+        constexpr int NCH = EPI == EPI_CRT ? 16 : 8;
+        const int ch0     = EPI == EPI_CRT ? 0 : (warp >= 8 ? 8 : 0);
         for (uint32_t it = 0; next_work(args, it, tm, tn, j); ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tcgen05_fence_after();
-
             const uint32_t row  = tm * BLOCK_M + q * 32 + lane;
             const uint32_t col0 = tn * BLOCK_N;
             const bool row_ok   = row < args.rowsA;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
 
+            // EPI_RESIDUE / EPI_CRT state that does not depend on the accumulator
+            const uint32_t row4 = tm * BLOCK_M + q * 32 + 4 * rg;
+            const bool rows4_ok = row4 < (uint32_t)args.ldc8u;   // the residue stacks are padded to 4 rows
+            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4;       // (re-read under EPI_CRT: no __restrict__)
+            uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4;
+            uint32_t old[RMW ? 4 * NCH : 1];
+            if constexpr (RMW) {   // complex passes: fetch the stored residues while the MMAs are still running
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const uint32_t col = col0 + 16 * (ch0 + c) + 4 * cg + jj;
+                        old[4 * c + jj] = (rows4_ok && col < args.rowsB) ? __ldcg(reinterpret_cast<const uint32_t *>(out4 + (size_t)col * args.ldc8u)) : 0u;
+                    }
+            }
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+
             if constexpr (EPI == EPI_RESIDUE || EPI == EPI_CRT) {
                 const uint32_t mj  = args.first_modulus + j;
                 const int32_t m    = dev_tab::OZ_MOD[mj];
                 const int32_t inv  = (int32_t)(4294967296ull / (uint32_t)m);
-                uint8_t *out = args.C8u + (size_t)j * args.sizeC + row;  // (re-read below under EPI_CRT: no __restrict__)
-                uint8_t *aux = args.C8u_aux + (size_t)j * args.sizeC + row;
                 const int rc = args.combine;
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 16) {
+#pragma unroll(RMW ? NCH : 1)
+                for (int c = 0; c < NCH; ++c) {
                     uint32_t v[16];
-                    tmem_ld16(taddr + c, v);
+                    tmem_ld16(taddr + 16 * (ch0 + c), v);
                     tmem_ld_wait();
-                    if (row_ok) {
+                    uint32_t r[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const uint32_t col = col0 + c + e;
+                    for (int e = 0; e < 16; ++e) r[e] = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
+                    __syncwarp();   // the previous chunk's scratch reads are done
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        scr[5 * lane + w] = r[4 * w] | (r[4 * w + 1] << 8) | (r[4 * w + 2] << 16) | (r[4 * w + 3] << 24);
+                    __syncwarp();
+                    const uint32_t w0 = scr[5 * (4 * rg) + cg], w1 = scr[5 * (4 * rg + 1) + cg];
+                    const uint32_t w2 = scr[5 * (4 * rg + 2) + cg], w3 = scr[5 * (4 * rg + 3) + cg];
+                    // 4 x 4 byte transpose: o[jj] = residues of rows 4rg .. 4rg+3 in column 4cg + jj
+                    const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                    const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                    uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
+                                     __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+                    if (rows4_ok) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const uint32_t col = col0 + 16 * (ch0 + c) + 4 * cg + jj;
                             if (col < args.rowsB) {
-                                uint32_t r = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
-                                if (rc != RC_STORE) r = combine_residue(rc, r, out + (size_t)col * args.ldc8u, aux + (size_t)col * args.ldc8u, m);
-                                out[(size_t)col * args.ldc8u] = (uint8_t)r;
+                                if constexpr (RMW) {
+                                    uint32_t ax;
+                                    o[jj] = combine_word(rc, o[jj], old[4 * c + jj], ax, m);
+                                    if (rc == RC_KARATSUBA_F) *reinterpret_cast<uint32_t *>(aux4 + (size_t)col * args.ldc8u) = ax;
+                                }
+                                *reinterpret_cast<uint32_t *>(out4 + (size_t)col * args.ldc8u) = o[jj];
                             }
                         }
                     }
@@ -332,7 +398,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             } else if constexpr (EPI == EPI_INT32) {
                 int32_t *__restrict__ out = args.C32i + row;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 16) {
+                for (int c = 16 * ch0; c < 16 * (ch0 + NCH); c += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
                     tmem_ld_wait();
@@ -347,7 +413,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             } else {  // EPI_ABSMAX
                 int32_t rmax = 0;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 16) {
+                for (int c = 16 * ch0; c < 16 * (ch0 + NCH); c += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
                     tmem_ld_wait();
@@ -539,7 +605,7 @@ int sm_count() {
     return n;
 }
 
-template <int EPI, typename T = double, bool SPLIT = false>
+template <int EPI, typename T = double, bool SPLIT = false, bool RMW = false>
 cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, BLOCK_M)) return cudaErrorInvalidValue;
@@ -547,7 +613,7 @@ cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     const char *dbg = getenv("OZ_DEBUG_SCHED");   // tuning knob: "tile" forces the tile-major schedule, "skipcrt" idles the CRT warps
     KernelArgs a = make_args(p, EPI == EPI_CRT || (dbg && strstr(dbg, "tile")));
     a.debug_skip_crt = (dbg && strstr(dbg, "skipcrt")) ? 1 : 0;
-    auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT>;
+    auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT, RMW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
@@ -570,7 +636,7 @@ cudaError_t launch_simt_t(const GemmProblem &p, cudaStream_t st) {
 cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStream_t st) {
     if (p.rowsA == 0 || p.rowsB == 0 || p.num_slices == 0) return cudaSuccess;
     switch (epi) {
-        case EPI_RESIDUE: return launch_tc<EPI_RESIDUE>(p, st);
+        case EPI_RESIDUE: return p.combine == RC_STORE ? launch_tc<EPI_RESIDUE>(p, st) : launch_tc<EPI_RESIDUE, double, false, true>(p, st);
         case EPI_INT32:   return launch_tc<EPI_INT32>(p, st);
         case EPI_ABSMAX:  return launch_tc<EPI_ABSMAX>(p, st);
         case EPI_CRT:

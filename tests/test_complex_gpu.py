@@ -55,9 +55,10 @@ CASES = [
     (64, 48, 64, 6, 1, 1, 0, "complex64", "complex128", "complex64", BIG),
     (96, 80, 112, 14, 0, 0, 0, "complex128", "complex128", "complex128", BIG),      # accurate mode
     (96, 80, 112, 15, 0, 0, 0, "complex64", "complex64", "complex64", KARA),        # one_accuracy_complex.cu's setting
-    # accurate big-matrix with a transposed A: the reference passes n where m is meant for the row offset of the
-    # lower block row of its bound matrix (scaling.hpp:3201,3204), so its shifts are only meaningful for m == n
-    (52, 52, 100, 8, 0, 1, 2, "complex128", "complex128", "complex128", BIG),
+    # (accurate big-matrix with a transposed / conjugated A is not comparable: the reference takes the maxima for
+    #  A's shifts from COLUMNS of the bound product there, scaling.hpp:3234 -> :2769-2783, and offsets the lower block
+    #  row of its bound matrix by n instead of m, :3201; covered by test_accurate_bigmatrix_transposed_a below)
+    (60, 44, 96, 9, 0, 1, 0, "complex128", "complex128", "complex128", KARA),       # accurate, transposed A, separate stacks
     (70, 52, 100, 8, 0, 0, 2, "complex128", "complex128", "complex128", BIG),
     (70, 52, 100, 8, 0, 0, 2, "complex128", "complex128", "complex128", CLASSIC),
     (1, 1, 1, 14, 1, 0, 0, "complex128", "complex128", "complex128", KARA),
@@ -92,6 +93,15 @@ def test_complex_against_unmodified_reference(g, oracle, m, n, k, N, fast, opA, 
     ref_writes_c = ct == BIG or N <= 7 or dC == torch.complex64
     if not ref_writes_c:
         assert (Cr == 0).all()          # the defect: C untouched
+        if not fast and opA != 0:
+            # ... and its big-matrix accurate mode is unusable for a transposed A (shifts from the wrong maxima: the
+            # result is off by percents), so the truth here is the native product
+            MA, MB = A.T, B.T
+            OA = MA if opA == 0 else MA.T if opA == 1 else MA.conj().T
+            OB = MB if opB == 0 else MB.T if opB == 1 else MB.conj().T
+            truth = (OA @ OB).T
+            assert ((C - truth).abs() / truth.abs()).max().item() < (1e-9 if N >= 12 else 1e-5)
+            return
         wsb = g.workSize(m, n, k, N, BIG)
         Cr, _ = run(oracle.ref_gemm, wsb, g, m, n, k, N, fast, A, B, opA, opB, dC, BIG)
     assert torch.equal(torch.view_as_real(C), torch.view_as_real(Cr))
@@ -110,6 +120,27 @@ def test_complex_alpha_beta(g, ct, alpha, beta):
     C, _ = run(ours(g), ws, g, m, n, k, N, True, A, B, 0, 0, torch.complex128, ct, alpha=alpha, beta=beta, C0=C0)
     want = alpha * P + beta * C0
     assert torch.allclose(C, want, rtol=1e-14, atol=0)     # a few ulp: fma vs separate rounding
+
+
+def test_accurate_bigmatrix_transposed_a(g):
+    """Accurate mode, big matrix, op_A = T / C: shifts must equal those of the separate-stack modes (same bound
+    product), and the result must be as accurate as theirs."""
+    torch = torch_()
+    m, n, k, N = 70, 52, 100, 10
+    for opA in (1, 2):
+        A, B = operands(g, m, n, k, opA, 2, torch.complex128, torch.complex128)
+        Cb, vb = run(ours(g), g.workSize(m, n, k, N, BIG), g, m, n, k, N, False, A, B, opA, 2, torch.complex128, BIG)
+        Ck, vk = run(ours(g), g.workSize(m, n, k, N, KARA), g, m, n, k, N, False, A, B, opA, 2, torch.complex128, KARA)
+        assert torch.equal(vb["sftA"], vk["sftA"]) and torch.equal(vb["sftB"], vk["sftB"])
+        assert torch.equal(torch.view_as_real(Cb), torch.view_as_real(Ck))
+        # column-major stored X (r x c) appears as a torch tensor of shape (c, r): math matrix = tensor.T
+        MA = A.T                                     # math A (k x m)
+        MB = B.T                                     # math B (n x k)
+        OA = MA.T if opA == 1 else MA.conj().T       # op(A): m x k
+        OB = MB.conj().T                             # op(B) = B^H: k x n
+        truth = OA @ OB                              # m x n
+        err = ((Cb.T - truth).abs() / truth.abs()).max().item()
+        assert err < 1e-7, err                       # 10 moduli: ~2e-9 (the reference's own accuracy at N = 10)
 
 
 @pytest.mark.parametrize("ct", [BIG, CLASSIC, KARA])
