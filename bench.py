@@ -279,7 +279,15 @@ def main():
         e2e_ms = e0.elapsed_time(e1) / ksteps
         out["e2e"] = {"value": flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": 8 * (m * k + k * n),
                       "d2h_bytes_per_step": 8 * m * n, "ms_per_step": e2e_ms, "steps": ksteps,
-                      "api": "gemmul8_b200_gemm_host (pinned host A, B, C)", "checksum": float(hC[::97, ::89].sum())}
+                      "api": "gemmul8_b200_gemm_host (pinned host A, B, C; 8 x 8 block wavefront: H2D, compute and D2H overlap)",
+                      "checksum": float(hC[::97, ::89].sum())}
+        # the same call with the copies in series (what a caller of the reference does around its gemm)
+        e0.record()
+        for _ in range(2):
+            g.gemm_host(0, 0, m, n, k, 1.0, hA, m, hB, k, 0.0, hC, m, N, fast, scratch, flags=g.FLAG_HOST_SERIAL)
+        e1.record()
+        torch.cuda.synchronize()
+        out["e2e"]["serial_copies_ms_per_step"] = e0.elapsed_time(e1) / 2
     elif multi:
         out["e2e"] = None
 

@@ -14,12 +14,17 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 namespace oz {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool encode_reference_chain() {
+    const char *e = getenv("GEMMUL8_B200_ENCODE");
+    return e && !strcmp(e, "reference");
+}
 }  // namespace oz
 
 namespace {
@@ -354,11 +359,151 @@ size_t gemmul8_b200_host_scratch_size(const gemmul8_b200_args *a) {
     return s + gemmul8_b200_worksize(a->m, a->n, a->k, a->num_moduli, a->compute_type);
 }
 
+// Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C.  The H2D
+// stream brings A row blocks and B column blocks alternately (A0, B0, A1, B1, ...); as soon as block
+// pair s is on the device the compute stream scales / encodes it and multiplies everything that has
+// become computable -- the column strip (rows 0..s, column block s) and the row strip (row block s,
+// column blocks 0..s-1) -- and the D2H stream returns each finished strip of C while the next blocks
+// are still arriving.  PCIe is full duplex, so the call ends about one strip after the last input
+// byte instead of after (inputs + compute + output) in series.
+static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
+    const size_t m = h->m, n = h->n, k = h->k;
+    const unsigned N = h->num_moduli, ti = N - 2;
+    cudaStream_t st = static_cast<cudaStream_t>(h->stream);
+    const size_t esA = elem_size(h->dtype_A), esB = elem_size(h->dtype_B), esC = elem_size(h->dtype_C);
+    const size_t colsA = h->op_A == GEMMUL8_OP_N ? k : m, colsB = h->op_B == GEMMUL8_OP_N ? n : k;
+    uint8_t *p = static_cast<uint8_t *>(dev_scratch);
+    uint8_t *dA = p; p += ceil_to(h->lda * colsA * esA, 256);
+    uint8_t *dB = p; p += ceil_to(h->ldb * colsB * esB, 256);
+    uint8_t *dC = p; p += ceil_to(h->ldc * n * esC, 256);
+    uint8_t *work = p;
+    oz::Layout L;
+    compute_layout(m, n, k, N, GEMMUL8_REAL_DEFAULT, L);
+    int8_t *A8i   = reinterpret_cast<int8_t *>(work + L.off_A8i);
+    int8_t *B8i   = reinterpret_cast<int8_t *>(work + L.off_B8i);
+    uint8_t *C8u  = work + L.off_C8u;
+    int16_t *sftA = reinterpret_cast<int16_t *>(work + L.off_sftA);
+    int16_t *sftB = reinterpret_cast<int16_t *>(work + L.off_sftB);
+    const bool a_strided = h->op_A == GEMMUL8_OP_N, b_strided = h->op_B != GEMMUL8_OP_N;
+    const int ref_width  = oz::ref_reduce_width(h->dtype_A, h->dtype_B, h->dtype_C);
+    const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
+    const bool split     = oz::host_tab::OZ_M_LO[ti] != 0.0 && h->dtype_C == GEMMUL8_F64;
+
+    // block boundaries: multiples of 256 rows / columns (whole GEMM tiles), at most 8 blocks per side
+    auto bounds = [](size_t len, size_t *b) -> int {
+        const size_t tiles = (len + 255) / 256;
+        const int S = (int)(tiles < 8 ? tiles : 8);
+        for (int i = 0; i <= S; ++i) { size_t x = (tiles * i / S) * 256; b[i] = x < len ? x : len; }
+        b[S] = len;
+        return S;
+    };
+    size_t rb[9], cb[9];
+    const int SR = bounds(m, rb), SC = bounds(n, cb);
+    const int S = SR > SC ? SR : SC;
+
+    struct Res {
+        cudaStream_t in = nullptr, out = nullptr;
+        cudaEvent_t evA[8], evB[8], evC[16], start;
+        int nev = 0;
+        ~Res() {
+            for (int i = 0; i < nev; ++i) { cudaEventDestroy(evA[i]); cudaEventDestroy(evB[i]); cudaEventDestroy(evC[2 * i]); cudaEventDestroy(evC[2 * i + 1]); }
+            if (nev) cudaEventDestroy(start);
+            if (in) cudaStreamDestroy(in);
+            if (out) cudaStreamDestroy(out);
+        }
+    } r;
+    OZ_CUDA(cudaStreamCreateWithFlags(&r.in, cudaStreamNonBlocking), "stream");
+    OZ_CUDA(cudaStreamCreateWithFlags(&r.out, cudaStreamNonBlocking), "stream");
+    OZ_CUDA(cudaEventCreateWithFlags(&r.start, cudaEventDisableTiming), "event");
+    for (int i = 0; i < 8; ++i) {
+        OZ_CUDA(cudaEventCreateWithFlags(&r.evA[i], cudaEventDisableTiming), "event");
+        OZ_CUDA(cudaEventCreateWithFlags(&r.evB[i], cudaEventDisableTiming), "event");
+        OZ_CUDA(cudaEventCreateWithFlags(&r.evC[2 * i], cudaEventDisableTiming), "event");
+        OZ_CUDA(cudaEventCreateWithFlags(&r.evC[2 * i + 1], cudaEventDisableTiming), "event");
+        r.nev = i + 1;
+    }
+    // the copies may not start before earlier work of the caller's stream on this scratch has finished
+    OZ_CUDA(cudaEventRecord(r.start, st), "event record");
+    OZ_CUDA(cudaStreamWaitEvent(r.in, r.start, 0), "stream wait");
+
+    auto copy_block = [&](uint8_t *dst, const void *src_, size_t ld, size_t es, bool rows, size_t lo, size_t hi, size_t other,
+                          cudaMemcpyKind kind, cudaStream_t s) -> cudaError_t {
+        // rows == true: rows [lo, hi) of a column-major matrix with `other` columns (strided); else columns [lo, hi)
+        if (hi <= lo) return cudaSuccess;
+        const uint8_t *src = static_cast<const uint8_t *>(src_);
+        if (rows) return cudaMemcpy2DAsync(dst + lo * es, ld * es, src + lo * es, ld * es, (hi - lo) * es, other, kind, s);
+        return cudaMemcpyAsync(dst + lo * ld * es, src + lo * ld * es, (hi - lo) * ld * es, kind, s);
+    };
+
+    oz::GemmProblem gp{};
+    gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
+    gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    auto strip = [&](size_t r0, size_t r1, size_t c0, size_t c1, cudaEvent_t done) -> int {
+        if (r1 <= r0 || c1 <= c0) return GEMMUL8_OK;
+        gp.A8i = A8i + r0 * L.lda8i; gp.rowsA = r1 - r0;
+        gp.B8i = B8i + c0 * L.lda8i; gp.rowsB = c1 - c0;
+        gp.C8u = C8u + c0 * L.m_pad + r0;
+        OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+        OZ_CUDA(oz::launch_crt(h->dtype_C, split, N, r1 - r0, c1 - c0, gp.C8u, L.m_pad, L.sizeC, dC + (c0 * h->ldc + r0) * esC, h->ldc,
+                               sftA + r0, sftB + c0, h->alpha, h->beta, st), "crt");
+        OZ_CUDA(cudaEventRecord(done, st), "event record");
+        OZ_CUDA(cudaStreamWaitEvent(r.out, done, 0), "stream wait");
+        // rows [r0, r1) of columns [c0, c1) of C
+        OZ_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t *>(h->C) + (c0 * h->ldc + r0) * esC, h->ldc * esC, dC + (c0 * h->ldc + r0) * esC,
+                                  h->ldc * esC, (r1 - r0) * esC, c1 - c0, cudaMemcpyDeviceToHost, r.out), "D2H C");
+        return GEMMUL8_OK;
+    };
+
+    for (int s = 0; s < S; ++s) {
+        const size_t r0 = s < SR ? rb[s] : m, r1 = s < SR ? rb[s + 1] : m;
+        const size_t c0 = s < SC ? cb[s] : n, c1 = s < SC ? cb[s + 1] : n;
+        OZ_CUDA(copy_block(dA, h->A, h->lda, esA, a_strided, r0, r1, colsA, cudaMemcpyHostToDevice, r.in), "H2D A");
+        OZ_CUDA(cudaEventRecord(r.evA[s], r.in), "event record");
+        OZ_CUDA(copy_block(dB, h->B, h->ldb, esB, b_strided, c0, c1, colsB, cudaMemcpyHostToDevice, r.in), "H2D B");
+        OZ_CUDA(cudaEventRecord(r.evB[s], r.in), "event record");
+    }
+    for (int s = 0; s < S; ++s) {
+        const size_t r0 = s < SR ? rb[s] : m, r1 = s < SR ? rb[s + 1] : m;
+        const size_t c0 = s < SC ? cb[s] : n, c1 = s < SC ? cb[s + 1] : n;
+        OZ_CUDA(cudaStreamWaitEvent(st, r.evA[s], 0), "stream wait");
+        if (r1 > r0) {
+            const uint8_t *Ax = dA + (a_strided ? r0 : r0 * h->lda) * esA;
+            int rc = scale_operand(h->dtype_A, a_strided, Ax, h->lda, r1 - r0, k, ref_width, l2, N, A8i + r0 * L.lda8i, L.lda8i, L.sizeA,
+                                   sftA + r0, true, st);
+            if (rc) return rc;
+        }
+        OZ_CUDA(cudaStreamWaitEvent(st, r.evB[s], 0), "stream wait");
+        if (c1 > c0) {
+            const uint8_t *Bx = dB + (b_strided ? c0 : c0 * h->ldb) * esB;
+            int rc = scale_operand(h->dtype_B, b_strided, Bx, h->ldb, c1 - c0, k, ref_width, l2, N, B8i + c0 * L.lda8i, L.lda8i, L.sizeB,
+                                   sftB + c0, true, st);
+            if (rc) return rc;
+        }
+        int rc = strip(0, r1, c0, c1, r.evC[2 * s]);          // column strip: all rows so far x the new column block
+        if (rc) return rc;
+        rc = strip(r0, r1, 0, c0, r.evC[2 * s + 1]);          // row strip: the new row block x the earlier column blocks
+        if (rc) return rc;
+    }
+    OZ_CUDA(cudaStreamSynchronize(r.out), "sync");
+    OZ_CUDA(cudaStreamSynchronize(st), "sync");
+    return GEMMUL8_OK;
+}
+
 int gemmul8_b200_gemm_host(gemmul8_b200_args *h, void *dev_scratch) {
     int rc = check_args(h);
     if (rc) return rc;
+    if (h) for (double &t : h->timers_ns) t = 0.0;
     if (!dev_scratch) return fail(GEMMUL8_ERR_ARGUMENT, "null scratch");
+    if (h->m == 0 || h->n == 0) return GEMMUL8_OK;
     cudaStream_t st = static_cast<cudaStream_t>(h->stream);
+    bool beta_zero = true;
+    const size_t es = elem_size(h->dtype_C);
+    for (size_t i = 0; i < es; ++i) beta_zero &= static_cast<const unsigned char *>(h->beta)[i] == 0;
+    if (!is_complex(h->dtype_C) && h->fastmode && beta_zero && h->k > 0 &&
+        !(h->flags & (GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_STAGE_SCALING | GEMMUL8_FLAG_STAGE_RESIDUES | GEMMUL8_FLAG_GEMM_SIMT |
+                      GEMMUL8_FLAG_FUSED_CRT | GEMMUL8_FLAG_HOST_SERIAL)))
+        return gemm_host_pipelined(h, dev_scratch);
+    // everything else (accurate mode needs all of A and B before the first shift; complex; beta != 0): in series
     const size_t colsA = h->op_A == GEMMUL8_OP_N ? h->k : h->m, colsB = h->op_B == GEMMUL8_OP_N ? h->n : h->k;
     const size_t bytesA = h->lda * colsA * elem_size(h->dtype_A), bytesB = h->ldb * colsB * elem_size(h->dtype_B);
     const size_t bytesC = h->ldc * h->n * elem_size(h->dtype_C);
@@ -370,9 +515,6 @@ int gemmul8_b200_gemm_host(gemmul8_b200_args *h, void *dev_scratch) {
     d.A = dA; d.B = dB; d.C = dC; d.work = p;
     OZ_CUDA(cudaMemcpyAsync(dA, h->A, bytesA, cudaMemcpyHostToDevice, st), "H2D A");
     OZ_CUDA(cudaMemcpyAsync(dB, h->B, bytesB, cudaMemcpyHostToDevice, st), "H2D B");
-    bool beta_zero = true;
-    const size_t es = elem_size(h->dtype_C);
-    for (size_t i = 0; i < es; ++i) beta_zero &= static_cast<const unsigned char *>(h->beta)[i] == 0;
     if (!beta_zero) OZ_CUDA(cudaMemcpyAsync(dC, h->C, bytesC, cudaMemcpyHostToDevice, st), "H2D C");
     rc = gemmul8_b200_gemm(&d);
     memcpy(h->timers_ns, d.timers_ns, sizeof(d.timers_ns));

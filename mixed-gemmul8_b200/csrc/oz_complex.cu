@@ -52,27 +52,18 @@ template <int G> __device__ __forceinline__ void store_group(int8_t *dst, const 
 
 // G consecutive positions i0 .. i0+G-1 of vector `vec`, modulus j.  re / im hold G scaled, truncated
 // values each (zeros beyond k); `sgn` = -1 for a conjugated operand.
-template <typename R, int G>
+template <typename R, int G, bool SPLIT>
 __device__ __forceinline__ void encode_group(const CplxSink &s, size_t vec, size_t i0, const R (&re)[G], const R (&im)[G],
-                                             int sgn, unsigned num_moduli) {
-    bool small = true;
-#pragma unroll
-    for (int e = 0; e < G; ++e) small &= fabs(re[e]) < SmallLimit<R>::value && fabs(im[e]) < SmallLimit<R>::value;
-    int lo_re[G], lo_im[G];
-    if (small) {
-#pragma unroll
-        for (int e = 0; e < G; ++e) { lo_re[e] = low_word(re[e]); lo_im[e] = low_word(im[e]); }
-    }
+                                             int sgn, unsigned num_moduli, bool ref_chain) {
     const int first  = (int)min((size_t)G, s.k > i0 ? s.k - i0 : (size_t)0);                          // positions < k
     const int second = (int)min((size_t)G, s.ld8i - s.k > i0 ? s.ld8i - s.k - i0 : (size_t)0);        // positions < ld8i - k
-    for (unsigned j = 0; j < num_moduli; ++j) {
-        const ModConst c = load_mod(j);
+    R both[2 * G];
+#pragma unroll
+    for (int e = 0; e < G; ++e) { both[e] = re[e]; both[G + e] = im[e]; }
+    residues_of<2 * G, SPLIT>(both, num_moduli, ref_chain, [&](unsigned j, const int (&q)[2 * G]) {
         int rr[G], ri[G];
 #pragma unroll
-        for (int e = 0; e < G; ++e) {
-            rr[e] = small ? residue_small(re[e], lo_re[e], c) : residue(re[e], c);
-            ri[e] = sgn * (small ? residue_small(im[e], lo_im[e], c) : residue(im[e], c));
-        }
+        for (int e = 0; e < G; ++e) { rr[e] = q[e]; ri[e] = sgn * q[G + e]; }
         uint32_t pr[G / 4], pi[G / 4];
 #pragma unroll
         for (int q = 0; q < G / 4; ++q) {
@@ -100,14 +91,14 @@ __device__ __forceinline__ void encode_group(const CplxSink &s, size_t vec, size
                 store_group<G>(row2 + s.k + i0, pr, second);
             }
         }
-    }
+    });
 }
 
 // contiguous vectors: one thread = 4 consecutive elements of one vector; grid = (ceil(ld8i/4/256), nvec)
-template <typename T>
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(256) encode_cplx_contig_kernel(const T *__restrict__ X, size_t ld, size_t len,
                                                                  const int16_t *__restrict__ sft_neg, unsigned num_moduli,
-                                                                 CplxSink sink, int sgn) {
+                                                                 CplxSink sink, int sgn, bool ref_chain) {
     using R = typename CReal<T>::type;
     const size_t vec = blockIdx.y;
     const size_t i0  = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
@@ -121,15 +112,15 @@ __global__ void __launch_bounds__(256) encode_cplx_contig_kernel(const T *__rest
         if (i0 + e < len) { const T x = p[i0 + e]; re[e] = scale(x.x); im[e] = scale(x.y); }
         else { re[e] = R(0); im[e] = R(0); }
     }
-    encode_group<R, 4>(sink, vec, i0, re, im, sgn, num_moduli);
+    encode_group<R, 4, SPLIT>(sink, vec, i0, re, im, sgn, num_moduli, ref_chain);
 }
 
 // strided vectors: tile of 32 vectors x 64 k through shared memory (lane == vector on the way in,
 // 8 consecutive k per thread on the way out); grid = (ceil(ld8i/64), ceil(nvec/32)), 256 threads
-template <typename T>
-__global__ void __launch_bounds__(256) encode_cplx_strided_kernel(const T *__restrict__ X, size_t ld, size_t nvec, size_t len,
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(256, 2) encode_cplx_strided_kernel(const T *__restrict__ X, size_t ld, size_t nvec, size_t len,
                                                                   const int16_t *__restrict__ sft_neg, unsigned num_moduli,
-                                                                  CplxSink sink, int sgn) {
+                                                                  CplxSink sink, int sgn, bool ref_chain) {
     using R = typename CReal<T>::type;
     __shared__ R tile_re[64 * 32];
     __shared__ R tile_im[64 * 32];
@@ -163,7 +154,7 @@ __global__ void __launch_bounds__(256) encode_cplx_strided_kernel(const T *__res
         re[e] = tile_re[slot];
         im[e] = tile_im[slot];
     }
-    encode_group<R, 8>(sink, vec, i0, re, im, sgn, num_moduli);
+    encode_group<R, 8, SPLIT>(sink, vec, i0, re, im, sgn, num_moduli, ref_chain);
 }
 
 template <typename T>
@@ -173,7 +164,7 @@ cudaError_t run_encode_complex(bool strided, const void *X, size_t ld, size_t nv
     const T *x = static_cast<const T *>(X);
     if (strided) {
         dim3 grid((unsigned)((sink.ld8i + 63) / 64), (unsigned)((nvec + 31) / 32));
-        encode_cplx_strided_kernel<T><<<grid, 256, 0, st>>>(x, ld, nvec, len, sft_neg, N, sink, sgn);
+        (N >= 16 ? encode_cplx_strided_kernel<T, true> : encode_cplx_strided_kernel<T, false>)<<<grid, 256, 0, st>>>(x, ld, nvec, len, sft_neg, N, sink, sgn, encode_reference_chain());
         count_launch();
     } else {
         for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
@@ -182,7 +173,7 @@ cudaError_t run_encode_complex(bool strided, const void *X, size_t ld, size_t nv
             s.out_re += v0 * sink.ld8i;
             if (s.out_im) s.out_im += v0 * sink.ld8i;
             dim3 grid((unsigned)((sink.ld8i / 4 + 255) / 256), (unsigned)nv);
-            encode_cplx_contig_kernel<T><<<grid, 256, 0, st>>>(x + v0 * ld, ld, len, sft_neg + v0, N, s, sgn);
+            (N >= 16 ? encode_cplx_contig_kernel<T, true> : encode_cplx_contig_kernel<T, false>)<<<grid, 256, 0, st>>>(x + v0 * ld, ld, len, sft_neg + v0, N, s, sgn, encode_reference_chain());
             count_launch();
         }
     }

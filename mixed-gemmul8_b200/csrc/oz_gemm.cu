@@ -163,7 +163,7 @@ struct KernelArgs {
     uint32_t rowsA, rowsB, num_kb, first_modulus;
     uint32_t tile_major, num_slices;
     Sched sched;
-    uint8_t *C8u; size_t ldc8u, sizeC;
+    uint8_t *C8u; size_t ldc8u, sizeC; uint32_t rows_store;
     int combine; uint8_t *C8u_aux;
     int32_t *C32i; size_t ldc32i;
     int32_t *rowmax; int32_t *colmax;
@@ -338,7 +338,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
             // EPI_RESIDUE / EPI_CRT state that does not depend on the accumulator
             const uint32_t row4 = tm * BLOCK_M + q * 32 + 4 * rg;
-            const bool rows4_ok = row4 < (uint32_t)args.ldc8u;   // the residue stacks are padded to 4 rows
+            const bool rows4_ok = row4 < args.rows_store;   // rowsA rounded up to 4 (the residue stacks are padded to 4 rows)
             uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4;       // (re-read under EPI_CRT: no __restrict__)
             uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4;
             uint32_t old[RMW ? 4 * NCH : 1];
@@ -589,6 +589,7 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     a.C = p.C; a.ldc = p.ldc; a.sftA = p.sftA; a.sftB = p.sftB; a.alpha = p.alpha; a.beta = p.beta;
     a.ab_mode = alpha_beta_mode(p.alpha, p.beta);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
+    a.rows_store = (uint32_t)((p.rowsA + 3) / 4 * 4);   // a sub-block launch must not touch the rows below it
     a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
     a.C32i = p.C32i; a.ldc32i = p.ldc32i;
     a.rowmax = p.rowmax; a.colmax = p.colmax;

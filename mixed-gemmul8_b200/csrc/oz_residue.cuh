@@ -30,30 +30,33 @@ __device__ __forceinline__ ModConst load_mod(unsigned j) {
     c.rcpf   = OZ_RCP32[j];
     return c;
 }
-// The reference's operation sequence, instruction for instruction (any magnitude).
-__device__ __forceinline__ int residue(double a, const ModConst &c) {
+// The reference's operation sequence (scaling.hpp:215-230).  It ends on the exact symmetric residue
+// for every magnitude the scaling can produce (rint(a * rcp) is within a few units of a / m, every
+// fma in the chain is exact and the float passes fold the rest; checked against integer arithmetic
+// up to 2^79 in tests/test_oracle.py), so the encoders may take ANY exact route to the same byte.
+// Kept for the on-device cross-check (GEMMUL8_FLAG_ENCODE_REFERENCE).
+__device__ __forceinline__ int residue_reference(double a, const ModConst &c) {
     float t = __double2float_rn(fma(rint(__dmul_rn(a, c.rcp)), c.neg_m, a));
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
     return __float2int_rz(t);
 }
-__device__ __forceinline__ int residue(float a, const ModConst &c) {
+__device__ __forceinline__ int residue_reference(float a, const ModConst &c) {
     float t = __fmaf_rn(rintf(__fmul_rn(a, c.rcpf)), c.neg_mf, a);
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
     t       = __fmaf_rn(rintf(__fmul_rn(t, c.rcpf)), c.neg_mf, t);
     return __float2int_rz(t);
 }
-// Same low byte for |a| below SmallLimit with ONE fp instruction per (element, modulus) and no
-// conversion-pipe work (FRND / F2F / F2I issue at a quarter of the FP64 rate on sm_100 and bound
-// the reference's sequence).  Why the result is identical:
-//   * the reference ends on the symmetric residue of a mod m: its first remainder t = a - q*m is
-//     an exact integer, and the float passes that follow subtract / add m until |t| <= m/2 (t/m is
-//     a multiple of 1/m, so rintf can only tie for m = 256, where +-128 both wrap to int8 -128);
-//   * so ANY quotient q with |a - q*m| <= 1.5 m followed by "fold once towards zero from either
-//     side" lands on the same byte.  Here q = rint(a * rcp) comes out of the low word of
-//     fma(a, rcp, 1.5*2^52) (|a * rcp| < 2^51; |a/m - q| <= 0.5 + 2^-53 |a/m| < 0.6), and
-//     t = a - q*m is evaluated modulo 2^32 on the low words (|t| < 2^9, so nothing is lost).
+// The routes used instead: one fp instruction per (element, modulus) and no conversion-pipe work
+// (FRND / F2F / F2I issue at a quarter of the FP64 rate on sm_100 and bound the sequence above).
+//   * ANY quotient q with |a - q*m| <= 1.5 m followed by "fold once towards zero from either side"
+//     lands on the symmetric residue (ties only exist for m = 256, where +-128 are the same int8);
+//   * q = rint(a * rcp) comes out of the low word of fma(a, rcp, 1.5*2^52) (needs |a * rcp| < 2^51;
+//     |a/m - q| <= 0.5 + 2^-53 |a/m| < 0.6), and t = a - q*m is evaluated modulo 2^32 on the low
+//     words (|t| < 2^9, so nothing is lost).  Valid for |a| < 2^57 (fp64) / 2^24 (fp32);
+//   * larger values (more than 15 moduli) are split exactly as a = h * 2^32 + l, |h| < 2^57,
+//     |l| < 2^32, and joined as (res(h) * (2^32 mod m) + res(l)) mod m.
 template <typename R> struct SmallLimit;
 template <> struct SmallLimit<double> { static constexpr double value = 0x1p57; };
 template <> struct SmallLimit<float> { static constexpr float value = 0x1p24f; };
@@ -78,6 +81,101 @@ __device__ __forceinline__ int residue_small(float a, int a_lo, const ModConst &
     const int q = __float_as_int(__fmaf_rn(a, c.rcpf, 12582912.0f)) - 0x4B400000;  // 1.5 * 2^23
     return fold_once(q * c.neg_mi + a_lo, c.half, c.m);
 }
+// exact residue of an int t, |t| < 2^22, by the same trick in fp32
+__device__ __forceinline__ int residue_int(int t, const ModConst &c) {
+    const float f = __int_as_float(0x4B400000 + t) - 12582912.0f;
+    const int q   = __float_as_int(__fmaf_rn(f, c.rcpf, 12582912.0f)) - 0x4B400000;
+    return fold_once(q * c.neg_mi + t, c.half, c.m);
+}
+// |a| < 2^89 through the halves h = trunc(a / 2^32), l = a - h * 2^32
+__device__ __forceinline__ int residue_big(double h, int h_lo, double l, int l_lo, int pow32, const ModConst &c) {
+    return residue_int(residue_small(h, h_lo, c) * pow32 + residue_small(l, l_lo, c), c);
+}
+
+// Residues of G integer-valued elements for every modulus; `store(j, r)` receives the G residues of
+// modulus j (the low byte of each int is the int8 to write).  Per thread, one of the exact routes.
+// SPLIT = false: values beyond the short route take the reference's chain (rare below 16 moduli, and it
+// keeps the kernel at 64 registers); SPLIT = true (launched for 16+ moduli): they take the split route.
+template <int G, bool SPLIT, typename Store>
+__device__ __forceinline__ void residues_double(const double (&v)[G], unsigned num_moduli, bool reference_chain, Store &&store) {
+    bool small = true;
+#pragma unroll
+    for (int e = 0; e < G; ++e) small &= fabs(v[e]) < 0x1p57;
+    if (reference_chain || (!SPLIT && !small)) {
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            int r[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) r[e] = residue_reference(v[e], c);
+            store(j, r);
+        }
+    } else if (small) {
+        int lo[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) lo[e] = low_word(v[e]);
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            int r[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) r[e] = residue_small(v[e], lo[e], c);
+            store(j, r);
+        }
+    } else if constexpr (SPLIT) {
+        double h[G], l[G];
+        int hlo[G], llo[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) {
+            h[e]   = trunc(v[e] * 0x1p-32);
+            l[e]   = fma(h[e], -4294967296.0, v[e]);
+            hlo[e] = low_word(h[e]);
+            llo[e] = low_word(l[e]);
+        }
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            const int p32    = dev_tab::OZ_POW32[j];
+            int r[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) r[e] = residue_big(h[e], hlo[e], l[e], llo[e], p32, c);
+            store(j, r);
+        }
+    }
+}
+template <int G, bool SPLIT, typename Store>
+__device__ __forceinline__ void residues_of(const double (&v)[G], unsigned num_moduli, bool reference_chain, Store &&store) {
+    residues_double<G, SPLIT>(v, num_moduli, reference_chain, store);
+}
+template <int G, bool SPLIT, typename Store>
+__device__ __forceinline__ void residues_of(const float (&v)[G], unsigned num_moduli, bool reference_chain, Store &&store) {
+    bool small = true;
+#pragma unroll
+    for (int e = 0; e < G; ++e) small &= fabsf(v[e]) < 0x1p24f;
+    if (reference_chain) {
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            int r[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) r[e] = residue_reference(v[e], c);
+            store(j, r);
+        }
+    } else if (small) {
+        int lo[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) lo[e] = low_word(v[e]);
+        for (unsigned j = 0; j < num_moduli; ++j) {
+            const ModConst c = load_mod(j);
+            int r[G];
+#pragma unroll
+            for (int e = 0; e < G; ++e) r[e] = residue_small(v[e], lo[e], c);
+            store(j, r);
+        }
+    } else {   // an fp32 value beyond 2^24 is still an exact integer: widen and take the fp64 routes
+        double d[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) d[e] = (double)v[e];
+        residues_double<G, SPLIT>(d, num_moduli, false, store);
+    }
+}
+
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {  // low bytes, 3 PRMT
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }

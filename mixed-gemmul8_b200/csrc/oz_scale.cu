@@ -200,10 +200,10 @@ __global__ void __launch_bounds__(W) fast_shift_strided_kernel(const T *__restri
 // 2 x 16-byte loads in, one 4-byte store per modulus out, every warp store is a full 128-byte line).
 // grid = (ceil(ld8i/4 / 256), nvec)
 // ---------------------------------------------------------------------------------------------
-template <typename R>
-__global__ void __launch_bounds__(256) encode_contig_kernel(const R *__restrict__ X, size_t ld, size_t len,
+template <typename R, bool SPLIT>
+__global__ void __launch_bounds__(256, 4) encode_contig_kernel(const R *__restrict__ X, size_t ld, size_t len,
                                                             const int16_t *__restrict__ sft_neg, unsigned num_moduli,
-                                                            int8_t *__restrict__ out, size_t ld8i, size_t inc) {
+                                                            int8_t *__restrict__ out, size_t ld8i, size_t inc, bool ref_chain) {
     const size_t vec = blockIdx.y;
     const size_t g   = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 along k
     const size_t i0  = g * 4;
@@ -224,27 +224,12 @@ __global__ void __launch_bounds__(256) encode_contig_kernel(const R *__restrict_
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = (i0 + e < len) ? p[i0 + e] : R(0);
     }
-    bool small = true;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { v[e] = scale(v[e]); small &= fabs(v[e]) < SmallLimit<R>::value; }
+    for (int e = 0; e < 4; ++e) v[e] = scale(v[e]);
     int8_t *__restrict__ o = out + vec * ld8i + i0;
-    if (small) {
-        int lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) lo[e] = low_word(v[e]);
-        for (unsigned j = 0; j < num_moduli; ++j) {
-            const ModConst c = load_mod(j);
-            *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) =
-                pack4(residue_small(v[0], lo[0], c), residue_small(v[1], lo[1], c), residue_small(v[2], lo[2], c),
-                      residue_small(v[3], lo[3], c));
-        }
-    } else {
-        for (unsigned j = 0; j < num_moduli; ++j) {
-            const ModConst c = load_mod(j);
-            *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) =
-                pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
-        }
-    }
+    residues_of<4, SPLIT>(v, num_moduli, ref_chain, [&](unsigned j, const int (&r)[4]) {
+        *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) = pack4(r[0], r[1], r[2], r[3]);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,10 +239,10 @@ __global__ void __launch_bounds__(256) encode_contig_kernel(const R *__restrict_
 // consecutive k of one vector and stores 16 bytes per modulus (a warp writes 4 full 128-byte lines).
 // grid = (ceil(ld8i/128), ceil(nvec/32)), 256 threads
 // ---------------------------------------------------------------------------------------------
-template <typename R>
-__global__ void __launch_bounds__(256) encode_strided_kernel(const R *__restrict__ X, size_t ld, size_t nvec, size_t len,
+template <typename R, bool SPLIT>
+__global__ void __launch_bounds__(256, SPLIT ? 2 : 4) encode_strided_kernel(const R *__restrict__ X, size_t ld, size_t nvec, size_t len,
                                                              const int16_t *__restrict__ sft_neg, unsigned num_moduli,
-                                                             int8_t *__restrict__ out, size_t ld8i, size_t inc) {
+                                                             int8_t *__restrict__ out, size_t ld8i, size_t inc, bool ref_chain) {
     __shared__ R tile[128 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t v0 = (size_t)blockIdx.y * 32;
@@ -280,37 +265,14 @@ __global__ void __launch_bounds__(256) encode_strided_kernel(const R *__restrict
     const size_t kb  = k0 + 16 * g;
     if (vec >= nvec || kb >= ld8i) return;
     R v[16];
-    bool small = true;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        v[e] = tile[(16 * g + e) * 32 + ((r + 4 * g) & 31)];
-        small &= fabs(v[e]) < SmallLimit<R>::value;
-    }
+    for (int e = 0; e < 16; ++e) v[e] = tile[(16 * g + e) * 32 + ((r + 4 * g) & 31)];
     int8_t *__restrict__ o = out + vec * ld8i + kb;
-    if (small) {
-        int lo[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) lo[e] = low_word(v[e]);
-        for (unsigned j = 0; j < num_moduli; ++j) {
-            const ModConst c = load_mod(j);
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                w[e] = pack4(residue_small(v[4 * e], lo[4 * e], c), residue_small(v[4 * e + 1], lo[4 * e + 1], c),
-                             residue_small(v[4 * e + 2], lo[4 * e + 2], c), residue_small(v[4 * e + 3], lo[4 * e + 3], c));
-            *reinterpret_cast<uint4 *>(o + (size_t)j * inc) = make_uint4(w[0], w[1], w[2], w[3]);  // ld8i % 16 == 0 and kb % 16 == 0
-        }
-    } else {
-        for (unsigned j = 0; j < num_moduli; ++j) {
-            const ModConst c = load_mod(j);
-            uint4 w;
-            w.x = pack4(residue(v[0], c), residue(v[1], c), residue(v[2], c), residue(v[3], c));
-            w.y = pack4(residue(v[4], c), residue(v[5], c), residue(v[6], c), residue(v[7], c));
-            w.z = pack4(residue(v[8], c), residue(v[9], c), residue(v[10], c), residue(v[11], c));
-            w.w = pack4(residue(v[12], c), residue(v[13], c), residue(v[14], c), residue(v[15], c));
-            *reinterpret_cast<uint4 *>(o + (size_t)j * inc) = w;
-        }
-    }
+    residues_of<16, SPLIT>(v, num_moduli, ref_chain, [&](unsigned j, const int (&q)[16]) {
+        *reinterpret_cast<uint4 *>(o + (size_t)j * inc) =   // ld8i % 16 == 0 and kb % 16 == 0
+            make_uint4(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]), pack4(q[8], q[9], q[10], q[11]),
+                       pack4(q[12], q[13], q[14], q[15]));
+    });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -440,19 +402,21 @@ cudaError_t launch_fast_shifts(int dtype, bool strided, const void *X, size_t ld
 template <typename R>
 static cudaError_t run_encode(bool strided, const void *X, size_t ld, size_t nvec, size_t len, const int16_t *sft_neg,
                               unsigned num_moduli, int8_t *out, size_t ld8i, size_t inc, cudaStream_t st) {
+    const bool ref_chain = encode_reference_chain();
     if (nvec == 0) return cudaSuccess;
     if (strided) {
         dim3 grid((unsigned)((ld8i + 127) / 128), (unsigned)((nvec + 31) / 32));
-        encode_strided_kernel<R><<<grid, 256, 0, st>>>(static_cast<const R *>(X), ld, nvec, len, sft_neg, num_moduli,
-                                                       out, ld8i, inc);
+        auto kern = num_moduli >= 16 ? encode_strided_kernel<R, true> : encode_strided_kernel<R, false>;
+        kern<<<grid, 256, 0, st>>>(static_cast<const R *>(X), ld, nvec, len, sft_neg, num_moduli, out, ld8i, inc, ref_chain);
         count_launch();
     } else {
         // blockIdx.y is limited to 65535: walk the vectors in slabs
         for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
             const size_t nv = nvec - v0 < 65535 ? nvec - v0 : 65535;
             dim3 grid((unsigned)((ld8i / 4 + 255) / 256), (unsigned)nv);
-            encode_contig_kernel<R><<<grid, 256, 0, st>>>(static_cast<const R *>(X) + v0 * ld, ld, len, sft_neg + v0,
-                                                          num_moduli, out + v0 * ld8i, ld8i, inc);
+            auto kern = num_moduli >= 16 ? encode_contig_kernel<R, true> : encode_contig_kernel<R, false>;
+            kern<<<grid, 256, 0, st>>>(static_cast<const R *>(X) + v0 * ld, ld, len, sft_neg + v0, num_moduli, out + v0 * ld8i,
+                                       ld8i, inc, ref_chain);
             count_launch();
         }
     }

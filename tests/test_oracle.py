@@ -139,3 +139,36 @@ def test_zero_vectors_and_degenerate_shapes(oracle):
         C = np.zeros((nn, mm))
         oracle.gemm_real(0, 0, mm, nn, kk, 1.0, a, mm, b, kk, 0.0, C, mm, 16, 1)
         assert np.allclose(C, b @ a, rtol=1e-12)
+
+
+def test_reference_residue_chain_is_the_exact_symmetric_residue(oracle):
+    """mod_8i (GEMMul8/src/scaling.hpp:215-230), restated in oracle.c, against integer arithmetic for
+    magnitudes up to 2^79 (20 moduli): it always lands on the symmetric residue (the int8 wrap maps
+    +128 to -128 for modulus 256).  This is what allows the CUDA encoders to use shorter exact routes."""
+    import ctypes as C
+    L = oracle.cpu()
+    L.oracle_mod8_f.restype = C.c_int
+    L.oracle_mod8_f.argtypes = [C.c_float, C.c_uint]
+    L.oracle_mod8_d.restype = C.c_int
+    L.oracle_mod8_d.argtypes = [C.c_double, C.c_uint]
+    mods = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181, 179, 173]
+    rng = np.random.default_rng(1)
+
+    def canon(a, m):
+        r = a % m
+        if r > m // 2:
+            r -= m
+        return -128 if (m == 256 and r == 128) else r
+
+    for bits, fn, wide in ((24, L.oracle_mod8_f, False), (53, L.oracle_mod8_d, True)):
+        for ebits in range(1, 80):
+            for _ in range(60):
+                mant = int(rng.integers(1 << (bits - 1), 1 << bits))
+                e = ebits - bits
+                a = mant * (2 ** e) if e >= 0 else mant >> (-e)
+                a = -a if rng.random() < 0.5 else a
+                x = float(a) if wide else float(np.float32(a))
+                if int(x) != a:
+                    continue
+                for j in (0, 1, 5, 13, 19):
+                    assert fn(x, j) == canon(a, mods[j]), (a, mods[j])

@@ -78,6 +78,15 @@ REF_CASES = CASES + [
     (1111, 999, 1313, 6, 1, 0, 0, "float32", "float32", "float32"),
     (1111, 999, 1313, 13, 1, 0, 0, "float64", "float32", "float64"),
     (640, 640, 131072, 14, 1, 0, 0, "float64", "float64", "float64"),       # k at the documented maximum 2^17
+    # more than 15 moduli: scaled values exceed 2^57 and take the split route of the encoder
+    (500, 400, 1500, 16, 1, 0, 0, "float64", "float64", "float64"),
+    (500, 400, 1500, 17, 0, 1, 1, "float64", "float64", "float64"),
+    (500, 400, 1500, 18, 1, 0, 1, "float64", "float64", "float64"),
+    (500, 400, 1500, 19, 0, 0, 0, "float64", "float64", "float64"),
+    (500, 400, 1500, 20, 1, 1, 0, "float64", "float64", "float64"),
+    (500, 400, 1500, 19, 1, 0, 0, "float32", "float32", "float32"),          # fp32 values far beyond 2^24
+    (500, 400, 1500, 18, 1, 0, 0, "float32", "float64", "float64"),
+    (500, 400, 1500, 14, 1, 0, 0, "float64", "float32", "float64"),
 ]
 
 
@@ -190,6 +199,21 @@ def test_fused_crt_equals_unfused(g, m, n, k, N, dt, alpha, beta):
     assert torch.equal(C_f, C_u)
 
 
+def test_encoder_routes_equal_reference_instruction_sequence(g, monkeypatch):
+    """The short exact residue routes of the encoders (oz_residue.cuh) against the reference's own
+    rint / fma / float-pass sequence run on the device (GEMMUL8_B200_ENCODE=reference), all magnitudes."""
+    torch = torch_()
+    for (m, n, k, N, dt, phi) in [(300, 200, 700, 14, "float64", 0.5), (300, 200, 700, 20, "float64", 4.0),
+                                  (300, 200, 700, 6, "float32", 0.5), (300, 200, 700, 19, "float32", 1.5)]:
+        A, B = operands(g, m, n, k, 0, 0, getattr(torch, dt), getattr(torch, dt), phi=phi, seedB=31)
+        monkeypatch.delenv("GEMMUL8_B200_ENCODE", raising=False)
+        _, v = run_ours(g, m, n, k, N, True, A, B, flags=g.FLAG_STAGE_SCALING)
+        monkeypatch.setenv("GEMMUL8_B200_ENCODE", "reference")
+        _, w = run_ours(g, m, n, k, N, True, A, B, flags=g.FLAG_STAGE_SCALING)
+        monkeypatch.delenv("GEMMUL8_B200_ENCODE", raising=False)
+        assert torch.equal(v["A8i"][:, :m], w["A8i"][:, :m]) and torch.equal(v["B8i"], w["B8i"])
+
+
 def test_leading_dimensions_and_determinism(g):
     torch = torch_()
     m, n, k, N = 333, 222, 444, 14
@@ -244,6 +268,27 @@ def test_host_buffer_entry_equals_device_entry(g):
     scratch = torch.empty(g.host_scratch_size(0, 0, m, n, k, hA, m, hB, k, hC, m, N), dtype=torch.uint8, device="cuda")
     g.gemm_host(0, 0, m, n, k, 1.0, hA, m, hB, k, 0.0, hC, m, N, True, scratch)
     assert torch.equal(hC, C.cpu())
+
+
+@pytest.mark.parametrize("m,n,k,N,opA,opB,dt", [
+    (1000, 1500, 300, 14, 0, 0, "float64"),      # ragged blocks, more column blocks than row blocks
+    (2100, 700, 257, 9, 1, 1, "float64"),        # transposed operands: the strided / contiguous block copies swap
+    (777, 777, 640, 6, 0, 1, "float32"),
+    (100, 90, 50, 14, 0, 0, "float64"),          # a single block
+])
+def test_host_wavefront_equals_device_entry(g, m, n, k, N, opA, opB, dt):
+    """gemm_host's S x S wavefront (block copies overlapped with per-strip scaling, products and CRT)
+    against the plain device call and against the in-series host path: bit-identical C."""
+    torch = torch_()
+    A, B = operands(g, m, n, k, opA, opB, getattr(torch, dt), getattr(torch, dt), seedB=8)
+    C, _ = run_ours(g, m, n, k, N, True, A, B, opA, opB)
+    hA, hB = A.cpu().pin_memory(), B.cpu().pin_memory()
+    lda, ldb = A.shape[1], B.shape[1]
+    for flags in (0, g.FLAG_HOST_SERIAL):
+        hC = torch.full((n, m), 7.0, dtype=getattr(torch, dt)).pin_memory()
+        scratch = torch.empty(g.host_scratch_size(opA, opB, m, n, k, hA, lda, hB, ldb, hC, m, N), dtype=torch.uint8, device="cuda")
+        g.gemm_host(opA, opB, m, n, k, 1.0, hA, lda, hB, ldb, 0.0, hC, m, N, True, scratch, flags=flags)
+        assert torch.equal(hC, C.cpu()), flags
 
 
 def test_benchmark_size_properties(g):

@@ -254,6 +254,8 @@ def emit(t, path):
     s += arr("OZ_MOD", "int", t["mod"], str)
     s += arr("OZ_RCP64", "double", t["rcp64"], hx)
     s += arr("OZ_RCP32", "float", t["rcp32"], hxf)
+    # 2^32 mod m_j, symmetric representative: joins the two halves of values beyond 2^57 in the encoder
+    s += arr("OZ_POW32", "int", [((1 << 32) % m) - (m if ((1 << 32) % m) > m // 2 else 0) for m in t["mod"]], str)
     s += arr("OZ_M_HI", "double", t["M_hi"], hx)
     s += arr("OZ_M_LO", "double", t["M_lo"], hx)
     s += arr("OZ_INV_M", "double", t["invM"], hx)
