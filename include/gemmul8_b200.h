@@ -58,7 +58,8 @@ enum {
     GEMMUL8_FLAG_STAGE_RESIDUES = 1u << 5, /* run phases 0-2: ... + per-modulus products mod m_j      */
     GEMMUL8_FLAG_FUSED_CRT      = 1u << 6, /* one kernel for GEMM + residues + CRT (tile-major schedule) */
     GEMMUL8_FLAG_GEMM_SIMT      = 1u << 8, /* debug: use the CUDA-core int8 GEMM instead of tcgen05   */
-    GEMMUL8_FLAG_HOST_SERIAL    = 1u << 9  /* gemm_host: copy in, compute, copy out in series (no wavefront) */
+    GEMMUL8_FLAG_HOST_SERIAL    = 1u << 9, /* gemm_host: copy in, compute, copy out in series (no wavefront) */
+    GEMMUL8_FLAG_STRIPS         = 1u << 10 /* gemm: column-strip pipeline on three streams (measured slower) */
 };
 
 /* Arguments of one gemm call, in the reference's argument order (gemmul8.hpp:30-47). */

@@ -128,6 +128,96 @@ int scale_operand(int dtype, bool strided, const void *X, size_t ld, size_t nvec
     return GEMMUL8_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column-strip pipeline of the device-resident real fast-mode call.  The three phases of a strip
+// use different units (encode: FP64 + LSU, product: tensor, CRT: FP64 + LSU), so on three streams
+//     side stream B : shifts + residues of B columns [strip j+1]
+//     caller stream : shifts + residues of all of A, then the all-moduli product of strip j
+//     side stream C : CRT of strip j-1
+// run concurrently (the persistent GEMM CTAs use 48 registers per thread and leave room on every SM
+// for the encode / CRT blocks).  Streams and events are created once per host thread and device.
+// ---------------------------------------------------------------------------------------------
+struct SideStreams {
+    int device = -1;
+    cudaStream_t sB = nullptr, sC = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr, evB[8] = {}, evG[8] = {};
+    bool ok = false;
+    bool init() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        if (ok && dev == device) return true;
+        if (ok) return false;   // one device per host thread (a second one falls back to the serial path)
+        device = dev;
+        if (cudaStreamCreateWithFlags(&sB, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&sC, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&start, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) return false;
+        for (int i = 0; i < 8; ++i) {
+            if (cudaEventCreateWithFlags(&evB[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&evG[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        ok = true;
+        return true;
+    }
+};
+thread_local SideStreams g_side;
+
+int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
+    const size_t m = a->m, n = a->n, k = a->k;
+    const unsigned N = a->num_moduli, ti = N - 2;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    SideStreams &S = g_side;
+    uint8_t *work = static_cast<uint8_t *>(a->work);
+    int8_t *A8i   = reinterpret_cast<int8_t *>(work + L.off_A8i);
+    int8_t *B8i   = reinterpret_cast<int8_t *>(work + L.off_B8i);
+    uint8_t *C8u  = work + L.off_C8u;
+    int16_t *sftA = reinterpret_cast<int16_t *>(work + L.off_sftA);
+    int16_t *sftB = reinterpret_cast<int16_t *>(work + L.off_sftB);
+    const bool a_strided = a->op_A == GEMMUL8_OP_N, b_strided = a->op_B != GEMMUL8_OP_N;
+    const int ref_width  = oz::ref_reduce_width(a->dtype_A, a->dtype_B, a->dtype_C);
+    const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
+    const bool split     = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;
+    const size_t esB = elem_size(a->dtype_B), esC = elem_size(a->dtype_C);
+
+    size_t cb[9];
+    const size_t tiles = (n + 255) / 256;
+    for (int i = 0; i <= strips; ++i) { const size_t x = (tiles * i / strips) * 256; cb[i] = x < n ? x : n; }
+    cb[strips] = n;
+
+    OZ_CUDA(cudaEventRecord(S.start, st), "event record");
+    OZ_CUDA(cudaStreamWaitEvent(S.sB, S.start, 0), "stream wait");
+    for (int j = 0; j < strips; ++j) {
+        const size_t c0 = cb[j], c1 = cb[j + 1];
+        if (c1 > c0) {
+            const uint8_t *Bx = static_cast<const uint8_t *>(a->B) + (b_strided ? c0 : c0 * a->ldb) * esB;
+            int rc = scale_operand(a->dtype_B, b_strided, Bx, a->ldb, c1 - c0, k, ref_width, l2, N, B8i + c0 * L.lda8i, L.lda8i, L.sizeB,
+                                   sftB + c0, true, S.sB);
+            if (rc) return rc;
+        }
+        OZ_CUDA(cudaEventRecord(S.evB[j], S.sB), "event record");
+    }
+    int rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, l2, N, A8i, L.lda8i, L.sizeA, sftA, true, st);
+    if (rc) return rc;
+
+    oz::GemmProblem gp{};
+    gp.A8i = A8i; gp.rowsA = m; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
+    gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    for (int j = 0; j < strips; ++j) {
+        const size_t c0 = cb[j], c1 = cb[j + 1];
+        OZ_CUDA(cudaStreamWaitEvent(st, S.evB[j], 0), "stream wait");
+        if (c1 <= c0) continue;
+        gp.B8i = B8i + c0 * L.lda8i; gp.rowsB = c1 - c0; gp.C8u = C8u + c0 * L.m_pad;
+        OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+        OZ_CUDA(cudaEventRecord(S.evG[j], st), "event record");
+        OZ_CUDA(cudaStreamWaitEvent(S.sC, S.evG[j], 0), "stream wait");
+        OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, c1 - c0, gp.C8u, L.m_pad, L.sizeC, static_cast<uint8_t *>(a->C) + c0 * a->ldc * esC,
+                               a->ldc, sftA, sftB + c0, a->alpha, a->beta, S.sC), "crt");
+    }
+    OZ_CUDA(cudaEventRecord(S.done, S.sC), "event record");
+    OZ_CUDA(cudaStreamWaitEvent(st, S.done, 0), "stream wait");
+    return GEMMUL8_OK;
+}
+
 int gemm_real(gemmul8_b200_args *a) {
     const size_t m = a->m, n = a->n, k = a->k;
     const unsigned N = a->num_moduli, ti = N - 2;
@@ -146,6 +236,16 @@ int gemm_real(gemmul8_b200_args *a) {
     const int ref_width  = oz::ref_reduce_width(a->dtype_A, a->dtype_B, a->dtype_C);
     const bool simt      = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) != 0;
     auto gemm = simt ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
+
+    // opt-in (GEMMUL8_FLAG_STRIPS): the column-strip pipeline above.  Measured SLOWER than the phases in series on
+    // B200 (56.0 vs 51.2 ms at 16384^3, profiles/r01_gemm_schedule_variants.log): blocks of the side streams
+    // delay CTAs of the statically scheduled persistent GEMM, which costs more than the overlap saves.
+    const unsigned serial_flags = GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_STAGE_SCALING | GEMMUL8_FLAG_STAGE_RESIDUES | GEMMUL8_FLAG_FUSED_CRT |
+                                  GEMMUL8_FLAG_GEMM_SIMT;
+    if ((a->flags & GEMMUL8_FLAG_STRIPS) && a->fastmode && !(a->flags & serial_flags) && n >= 2048 && g_side.init()) {
+        const int strips = n >= 8192 ? 4 : 2;
+        return gemm_real_strips(a, L, strips);
+    }
 
     PhaseTimer timer((a->flags & GEMMUL8_FLAG_TIMERS) != 0, st);
     timer.mark();

@@ -214,6 +214,16 @@ def test_encoder_routes_equal_reference_instruction_sequence(g, monkeypatch):
         assert torch.equal(v["A8i"][:, :m], w["A8i"][:, :m]) and torch.equal(v["B8i"], w["B8i"])
 
 
+def test_strip_pipeline_equals_default(g):
+    """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
+    torch = torch_()
+    m, n, k, N = 1500, 4500, 700, 14
+    A, B = operands(g, m, n, k, 0, 1, torch.float64, torch.float64, seedB=12)
+    C, v = run_ours(g, m, n, k, N, True, A, B, 0, 1)
+    Cs, vs = run_ours(g, m, n, k, N, True, A, B, 0, 1, flags=g.FLAG_STRIPS)
+    assert torch.equal(v["C8u"][:, :, :m], vs["C8u"][:, :, :m]) and torch.equal(C, Cs)
+
+
 def test_leading_dimensions_and_determinism(g):
     torch = torch_()
     m, n, k, N = 333, 222, 444, 14
