@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--accurate", action="store_true", help="accurate mode instead of fast mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: ONE m = n = k = --size problem block-partitioned over the P x Q grid (BASELINE config 5: --size 65536) "
+                         "instead of the default weak scaling (one --size^2 block of C per GPU)")
     return ap.parse_args()
 
 
@@ -105,6 +108,18 @@ def peaks():
     return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(m_loc, n_loc, k, N):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/r01_ncu_full_v3_raw.csv, one launch at 16384^3, 14 moduli); null for other per-GPU shapes."""
+    if (m_loc, n_loc, k, N) != (16384, 16384, 16384, 14):
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return json.load(open(path))["oz_gemm_tcgen05_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def cpu_baseline(sample=1024):
     """The reference's host GEMM (double-double, OpenMP) restated in oracle.c, on this box's cores."""
     import numpy as np
@@ -159,7 +174,8 @@ def main():
     S = args.size
     sampler = ClockSampler(local_rank)
     out = {"metric": METRIC if N == 14 else f"effective FP64 TFLOPS (DGEMM emu, {N} moduli)", "unit": "TFLOPS", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
+           "vs_baseline": None,
            "dtype": "int8 (s8 x s8 -> s32 tensor cores) + f64 CRT", "data": "synthetic"}
 
     if args.impl == "reference":
@@ -169,7 +185,7 @@ def main():
         from importlib import import_module
         dmod = import_module("gemmul8_b200.distributed")
         grid = dmod.BlockGrid()
-        m, n, k = S * grid.P, S * grid.Q, S
+        m, n, k = (S, S, S) if args.strong else (S * grid.P, S * grid.Q, S)
         m_loc, n_loc = grid.block_dims(m, n)
         klo, khi = grid.a_slice_k(k)
         clo, chi = grid.b_slice_cols(n_loc)
@@ -204,17 +220,20 @@ def main():
     launches0 = g.launch_count()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phase = [0.0] * 4
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        t = step(g.FLAG_TIMERS)
-        phase = [a + b for a, b in zip(phase, t)]
+        step()                      # asynchronous calls, no instrumentation inside the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     launches = g.launch_count() - launches0
+    # per-phase split from a few instrumented calls outside the timed region (FLAG_TIMERS brackets the phases with events)
+    phase, psteps = [0.0] * 4, 3
+    for _ in range(psteps):
+        phase = [a + b for a, b in zip(phase, step(g.FLAG_TIMERS))]
+    barrier()
     if multi:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -227,18 +246,18 @@ def main():
     out.update({"value": flops / (ms_step * 1e-3) / 1e12, "ms_per_step": ms_step, "gpu_launches": launches, "clocks": clocks})
 
     # roofline of the dominant kernel (the all-moduli tcgen05 GEMM), from the live per-phase events
-    gemm_ms = phase[1] / args.steps / 1e6
+    gemm_ms = phase[1] / psteps / 1e6
     per_gpu_ops = 2.0 * N * (m * n * k / world)
     long_step = gemm_ms > 20.0
     peak = 2.0 * (bf16_sust if long_step else bf16_burst)
     ach = per_gpu_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                       "traffic": None, "kernel": "oz_gemm_tcgen05_kernel<EPI_RESIDUE> (all moduli, residues fused)", "kernel_ms": gemm_ms,
+                       "traffic": ncu_traffic(m_loc if multi else m, n_loc if multi else n, k, N), "kernel": "oz_gemm_tcgen05_kernel<EPI_RESIDUE> (all moduli, residues fused)", "kernel_ms": gemm_ms,
                        "peak_source": f"2 x bf16 {'sustained' if long_step else 'burst'} of {peak_src}: kind::i8 issues at twice the bf16 rate",
                        "algorithmic_ops": "2*N*m*n*k int8 ops per launch"}
     enc_bytes = (8.0 * (m * k + k * n) * 2 + N * (m * k + k * n)) / world  # two passes over fp64 inputs + int8 slices out
-    scal_ms = phase[0] / args.steps / 1e6
-    out["phases_ms"] = {"scaling": scal_ms, "int8_gemm_fused_residue": gemm_ms, "crt_inverse_scaling": phase[3] / args.steps / 1e6,
+    scal_ms = phase[0] / psteps / 1e6
+    out["phases_ms"] = {"scaling": scal_ms, "int8_gemm_fused_residue": gemm_ms, "crt_inverse_scaling": phase[3] / psteps / 1e6,
                         "scaling_GBps": enc_bytes / (scal_ms * 1e-3) / 1e9 if scal_ms > 0 else None, "hbm_peak_GBps": hbm}
     out["config"] = {"workload": f"DGEMM emulation m={m} n={n} k={k}, {N} moduli, {'fast' if fast else 'accurate'} mode, phi={PHI}, ops N/N, alpha=1 beta=0",
                      "parallelism": f"{world} GPU(s)" + (f", {grid.P}x{grid.Q} C-block grid, NCCL all-gather of FP64 panels" if multi else ""),

@@ -59,7 +59,9 @@ enum {
     GEMMUL8_FLAG_FUSED_CRT      = 1u << 6, /* one kernel for GEMM + residues + CRT (tile-major schedule) */
     GEMMUL8_FLAG_GEMM_SIMT      = 1u << 8, /* debug: use the CUDA-core int8 GEMM instead of tcgen05   */
     GEMMUL8_FLAG_HOST_SERIAL    = 1u << 9, /* gemm_host: copy in, compute, copy out in series (no wavefront) */
-    GEMMUL8_FLAG_STRIPS         = 1u << 10 /* gemm: column-strip pipeline on three streams (measured slower) */
+    GEMMUL8_FLAG_STRIPS         = 1u << 10, /* gemm: column-strip pipeline on three streams (measured slower) */
+    GEMMUL8_FLAG_ONLY_SCALE_A   = 1u << 11, /* real types: shifts + residues of A only, then return (B may still be in flight) */
+    GEMMUL8_FLAG_SKIP_SCALE_A   = 1u << 12  /* real types: A's shifts + residues are already in `work` (previous flag)        */
 };
 
 /* Arguments of one gemm call, in the reference's argument order (gemmul8.hpp:30-47). */

@@ -253,11 +253,17 @@ int gemm_real(gemmul8_b200_args *a) {
     // ---------------- phase 0: scaling ----------------
     if (a->fastmode) {
         const float l2 = oz::host_tab::OZ_LOG2M_FAST[ti];
-        int rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, l2, N, A8i, L.lda8i, L.sizeA, sftA, true, st);
+        // (a distributed caller overlaps the arrival of the B panel with the scaling of A: two calls,
+        //  GEMMUL8_FLAG_ONLY_SCALE_A then GEMMUL8_FLAG_SKIP_SCALE_A; see mixed-gemmul8_b200/distributed.py)
+        int rc = GEMMUL8_OK;
+        if (!(a->flags & GEMMUL8_FLAG_SKIP_SCALE_A))
+            rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, l2, N, A8i, L.lda8i, L.sizeA, sftA, true, st);
         if (rc) return rc;
+        if (a->flags & GEMMUL8_FLAG_ONLY_SCALE_A) { timer.mark(); timer.finish(a->timers_ns); return GEMMUL8_OK; }
         rc = scale_operand(a->dtype_B, b_strided, a->B, a->ldb, n, k, ref_width, l2, N, B8i, L.lda8i, L.sizeB, sftB, true, st);
         if (rc) return rc;
     } else {
+        if (a->flags & GEMMUL8_FLAG_ONLY_SCALE_A) return GEMMUL8_OK;   // accurate mode needs both operands: all work in the second call
         // reference: int8tc::scaling, GEMMul8/src/scaling.hpp:3053-3136
         OZ_CUDA(oz::launch_bound_extract(a->dtype_A, a_strided, a->A, a->lda, m, k, A8i, L.lda8i, sftA, st), "bound extract A");
         OZ_CUDA(oz::launch_bound_extract(a->dtype_B, b_strided, a->B, a->ldb, n, k, B8i, L.lda8i, sftB, st), "bound extract B");

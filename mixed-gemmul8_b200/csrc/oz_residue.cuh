@@ -23,6 +23,7 @@ __device__ __forceinline__ ModConst load_mod(unsigned j) {
     c.m      = OZ_MOD[j];
     c.half   = c.m >> 1;
     c.neg_mi = -c.m;
+    asm volatile("" : "+r"(c.neg_mi));   // keep -m in a register: otherwise every q * (-m) becomes a negate + IMAD
     // int -> fp through the exponent trick (exact; keeps I2F off the conversion pipe)
     c.neg_m  = 4503599627370496.0 - __hiloint2double(0x43300000, c.m);
     c.rcp    = OZ_RCP64[j];
@@ -112,7 +113,10 @@ __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned n
     } else if (small) {
         int lo[G];
 #pragma unroll
-        for (int e = 0; e < G; ++e) lo[e] = low_word(v[e]);
+        for (int e = 0; e < G; ++e) {
+            lo[e] = low_word(v[e]);
+            asm volatile("" : "+r"(lo[e]));   // computed once: do not rematerialise the F2I inside the modulus loop
+        }
         for (unsigned j = 0; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
             int r[G];
@@ -129,6 +133,7 @@ __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned n
             l[e]   = fma(h[e], -4294967296.0, v[e]);
             hlo[e] = low_word(h[e]);
             llo[e] = low_word(l[e]);
+            asm volatile("" : "+r"(hlo[e]), "+r"(llo[e]));
         }
         for (unsigned j = 0; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
@@ -160,7 +165,10 @@ __device__ __forceinline__ void residues_of(const float (&v)[G], unsigned num_mo
     } else if (small) {
         int lo[G];
 #pragma unroll
-        for (int e = 0; e < G; ++e) lo[e] = low_word(v[e]);
+        for (int e = 0; e < G; ++e) {
+            lo[e] = low_word(v[e]);
+            asm volatile("" : "+r"(lo[e]));
+        }
         for (unsigned j = 0; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
             int r[G];

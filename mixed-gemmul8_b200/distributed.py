@@ -64,21 +64,22 @@ class BlockGrid:
         return self.p * w, (self.p + 1) * w
 
     # -- panel exchange --------------------------------------------------------------------
-    def gather_a_panel(self, a_slice, m_loc, k):
-        """a_slice: (k/Q, m_loc) tensor = column-major m_loc x k/Q block.  Returns the (k, m_loc) panel."""
+    def gather_a_panel(self, a_slice, m_loc, k, async_op=False):
+        """a_slice: (k/Q, m_loc) tensor = column-major m_loc x k/Q block.  Returns the (k, m_loc) panel
+        (and the NCCL work handle when async_op)."""
         if self.Q == 1:
-            return a_slice
+            return (a_slice, None) if async_op else a_slice
         out = torch.empty((k, m_loc), dtype=a_slice.dtype, device=a_slice.device)
-        dist.all_gather_into_tensor(out, a_slice.contiguous(), group=self.row_group)
-        return out
+        w = dist.all_gather_into_tensor(out, a_slice.contiguous(), group=self.row_group, async_op=async_op)
+        return (out, w) if async_op else out
 
-    def gather_b_panel(self, b_slice, n_loc, k):
+    def gather_b_panel(self, b_slice, n_loc, k, async_op=False):
         """b_slice: (n_loc/P, k) tensor = column-major k x n_loc/P block.  Returns the (n_loc, k) panel."""
         if self.P == 1:
-            return b_slice
+            return (b_slice, None) if async_op else b_slice
         out = torch.empty((n_loc, k), dtype=b_slice.dtype, device=b_slice.device)
-        dist.all_gather_into_tensor(out, b_slice.contiguous(), group=self.col_group)
-        return out
+        w = dist.all_gather_into_tensor(out, b_slice.contiguous(), group=self.col_group, async_op=async_op)
+        return (out, w) if async_op else out
 
 
 def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli, fastmode, work, flags=0):
@@ -86,7 +87,22 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
 
     a_slice / b_slice are this rank's pre-exchange pieces (see BlockGrid); returns the phase timers."""
     m_loc, n_loc = grid.block_dims(m, n)
-    a_panel = grid.gather_a_panel(a_slice, m_loc, k)
-    b_panel = grid.gather_b_panel(b_slice, n_loc, k)
-    return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
-                    num_moduli, fastmode, work, flags=flags)
+    overlap = fastmode and a_slice.is_cuda and not (flags & ~pkg.FLAG_TIMERS)
+    if not overlap:
+        a_panel = grid.gather_a_panel(a_slice, m_loc, k)
+        b_panel = grid.gather_b_panel(b_slice, n_loc, k)
+        return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
+                        num_moduli, fastmode, work, flags=flags)
+    # The row and the column communicator are different NCCL communicators with their own streams: both
+    # all-gathers run at the same time, and A's shifts + residues are computed while B is still arriving.
+    a_panel, wa = grid.gather_a_panel(a_slice, m_loc, k, async_op=True)
+    b_panel, wb = grid.gather_b_panel(b_slice, n_loc, k, async_op=True)
+    if wa is not None:
+        wa.wait()                                   # the compute stream waits for the panel; the host does not block
+    t0 = pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
+                  num_moduli, fastmode, work, flags=flags | pkg.FLAG_ONLY_SCALE_A)
+    if wb is not None:
+        wb.wait()
+    t1 = pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
+                  num_moduli, fastmode, work, flags=flags | pkg.FLAG_SKIP_SCALE_A)
+    return [x + y for x, y in zip(t0, t1)]

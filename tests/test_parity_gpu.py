@@ -214,6 +214,23 @@ def test_encoder_routes_equal_reference_instruction_sequence(g, monkeypatch):
         assert torch.equal(v["A8i"][:, :m], w["A8i"][:, :m]) and torch.equal(v["B8i"], w["B8i"])
 
 
+def test_two_call_split_equals_single_call(g):
+    """FLAG_ONLY_SCALE_A followed by FLAG_SKIP_SCALE_A (how distributed.pgemm overlaps the B panel's arrival with A's
+    scaling) leaves the same workspace and C as one call."""
+    torch = torch_()
+    m, n, k, N = 700, 500, 900, 14
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=12)
+    C, v = run_ours(g, m, n, k, N, True, A, B)
+    C2 = torch.zeros_like(C)
+    work = torch.zeros(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+    junk = torch.full_like(B, float("nan"))          # B "has not arrived yet" during the first call
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, junk, k, 0.0, C2, m, N, True, work, flags=g.FLAG_ONLY_SCALE_A)
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C2, m, N, True, work, flags=g.FLAG_SKIP_SCALE_A)
+    torch.cuda.synchronize()
+    w = g.work_views(work, g.work_layout(m, n, k, N), N, m, n)
+    assert torch.equal(w["A8i"][:, :m], v["A8i"][:, :m]) and torch.equal(w["B8i"], v["B8i"]) and torch.equal(C2, C)
+
+
 def test_strip_pipeline_equals_default(g):
     """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
     torch = torch_()
