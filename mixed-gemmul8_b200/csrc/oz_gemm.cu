@@ -286,9 +286,14 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * SMEM_STAGE;
+                    if (args.debug_skip_crt == 2 && (kb & 1)) {   // tuning experiment: what if half of the B traffic were shared?
+                        mbar_expect_tx(full_bar(stage), SMEM_A);
+                        tma_load_3d(sa, &map_a, full_bar(stage), (int)(kb * BLOCK_K), (int)(tm * BLOCK_M), (int)j);
+                    } else {
                     mbar_expect_tx(full_bar(stage), SMEM_STAGE);
                     tma_load_3d(sa, &map_a, full_bar(stage), (int)(kb * BLOCK_K), (int)(tm * BLOCK_M), (int)j);
                     tma_load_3d(sa + SMEM_A, &map_b, full_bar(stage), (int)(kb * BLOCK_K), (int)(tn * BLOCK_N), (int)j);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -519,6 +524,253 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
 }
 
+
+// =============================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) of the residue kernel: two CTAs on the SMs of one TPC share
+// a 256 x 256 tile.  Each CTA keeps its own 128 rows of A and HALF of the B tile (128 columns) in
+// shared memory; the tensor cores of the pair exchange the B halves, so per 256 x 256 x 128 block of
+// MACs the pair pulls 64 KB through L2 instead of the 96 KB two independent CTAs need.  The kernel
+// is power-bound on B200; whether the saved L2 traffic turns into clock is measured in DESIGN.md 3.4
+// (so far it does not: the variant is opt-in).
+//   every CTA    warp 0 : TMA producer of its own A rows and B half; the bytes are accounted on the
+//                         LEADER's full barrier (cp.async.bulk.tensor .cta_group::2)
+//   leader only  warp 1 : issues tcgen05.mma.cta_group::2 (M 256, N 256, K 32); its commits are
+//                         multicast to the empty / accumulator-full barriers of both CTAs
+//   every CTA    warp 2 : TMEM allocation (cta_group::2), warps 4-11: epilogue of its own 128 rows;
+//                         one lane per warp tells the leader that the accumulator buffer is drained
+// =============================================================================================
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_SMEM_A = BLOCK_M * BLOCK_K;          // 128 rows of A
+constexpr int PAIR_SMEM_B = 128 * BLOCK_K;              // 128 of the tile's 256 columns of B
+constexpr int PAIR_STAGE  = PAIR_SMEM_A + PAIR_SMEM_B;  // 32 KiB per CTA and stage
+constexpr int PAIR_SMEM_TOTAL = PAIR_STAGES * PAIR_STAGE + SMEM_BARRIERS + SMEM_SCRATCH + 1024;
+constexpr int PAIR_BAND = 8;                            // 256-row tiles per scheduling band
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory; the transaction bytes land on the barrier at `bar_cluster_addr`
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+struct PairSched {   // items = (256-row tile, column tile, modulus), ordered (band of 8 row tiles, modulus, column tile, row tile)
+    uint32_t tiles_m, tiles_n, slices, full_bands, per_band_full, total, band_m;
+    __host__ __device__ void init(uint32_t tm, uint32_t tn, uint32_t s, uint32_t band = PAIR_BAND) {
+        tiles_m = tm; tiles_n = tn; slices = s; band_m = band;
+        full_bands = tm / band_m;
+        per_band_full = band_m * tn * s;
+        total = tm * tn * s;
+    }
+    __device__ __forceinline__ void decode(uint32_t item, uint32_t &tm, uint32_t &tn, uint32_t &j) const {
+        uint32_t band = item / per_band_full, rem, bm;
+        if (band < full_bands) { rem = item - band * per_band_full; bm = band_m; }
+        else { band = full_bands; rem = item - full_bands * per_band_full; bm = tiles_m - full_bands * band_m; }
+        const uint32_t per_j = bm * tiles_n;
+        j = rem / per_j;
+        const uint32_t r2 = rem - j * per_j;
+        tn = r2 / bm;
+        tm = band * band_m + (r2 - tn * bm);
+    }
+};
+struct PairArgs {
+    uint32_t rowsA, rowsB, num_kb, first_modulus, rows_store;
+    PairSched sched;
+    uint8_t *C8u; size_t ldc8u, sizeC;
+    int combine; uint8_t *C8u_aux;
+    uint32_t debug_skew;
+};
+
+template <bool RMW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PairArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base  = smem_base + PAIR_STAGES * PAIR_STAGE;
+    auto full_bar   = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar  = [&](int s) { return bar_base + 8u * (PAIR_STAGES + s); };
+    auto tfull_bar  = [&](int s) { return bar_base + 8u * (2 * PAIR_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * PAIR_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * PAIR_STAGES + 4);
+    uint32_t *tmem_slot_ptr  = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank    = cluster_ctarank();         // 0 = leader
+    const uint32_t pair    = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t num_kb  = args.num_kb;
+    const uint32_t total   = args.sched.total;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }   // 8 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();          // barriers of both CTAs are initialised before anybody signals across the pair
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, tm, tn, j;
+            if (args.debug_skew) __nanosleep((pair % args.sched.band_m) * args.debug_skew);   // experiment: break the lockstep of the sharers
+            for (uint32_t item = pair; item < total; item += npairs) {
+                args.sched.decode(item, tm, tn, j);
+                const int rowA = (int)(tm * 256 + rank * 128), rowB = (int)(tn * BLOCK_N + rank * 128);
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa   = smem_base + stage * PAIR_STAGE;
+                    const uint32_t lbar = map_to_cta(full_bar(stage), 0);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * PAIR_STAGE);   // both CTAs' bytes
+                    tma_load_3d_pair(sa, &map_a, lbar, (int)(kb * BLOCK_K), rowA, (int)j);
+                    tma_load_3d_pair(sa + PAIR_SMEM_A, &map_b, lbar, (int)(kb * BLOCK_K), rowB, (int)j);
+                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(256, BLOCK_N);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t item = pair; item < total; item += npairs, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * PAIR_STAGE;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + PAIR_SMEM_A);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_i8_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | (uint32_t)k) != 0 ? 1u : 0u);
+                    tcgen05_commit_pair(empty_bar(stage));   // frees this stage in both CTAs
+                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit_pair(tfull_bar(acc));         // accumulator complete, both CTAs
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int q = warp & 3;
+        const int rg = lane & 7, cg = lane >> 3;
+        uint32_t *scr = reinterpret_cast<uint32_t *>(smem_raw + (bar_base + SMEM_BARRIERS - smem_u32(smem_raw))) + (warp - 4) * 160;
+        constexpr int NCH = 8;
+        const int ch0     = warp >= 8 ? 8 : 0;
+        uint32_t tm, tn, j, it = 0;
+        for (uint32_t item = pair; item < total; item += npairs, ++it) {
+            args.sched.decode(item, tm, tn, j);
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const uint32_t col0 = tn * BLOCK_N;
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+            const uint32_t row4 = tm * 256 + rank * 128 + q * 32 + 4 * rg;
+            const bool rows4_ok = row4 < args.rows_store;
+            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4;
+            uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4;
+            uint32_t old[RMW ? 4 * NCH : 1];
+            if constexpr (RMW) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const uint32_t col = col0 + 16 * (ch0 + c) + 4 * cg + jj;
+                        old[4 * c + jj] = (rows4_ok && col < args.rowsB) ? __ldcg(reinterpret_cast<const uint32_t *>(out4 + (size_t)col * args.ldc8u)) : 0u;
+                    }
+            }
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const uint32_t mj = args.first_modulus + j;
+            const int32_t m   = dev_tab::OZ_MOD[mj];
+            const int32_t inv = (int32_t)(4294967296ull / (uint32_t)m);
+            const int rc      = args.combine;
+#pragma unroll(RMW ? NCH : 1)
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t v[16];
+                tmem_ld16(taddr + 16 * (ch0 + c), v);
+                tmem_ld_wait();
+                uint32_t r[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
+                __syncwarp();
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    scr[5 * lane + w] = r[4 * w] | (r[4 * w + 1] << 8) | (r[4 * w + 2] << 16) | (r[4 * w + 3] << 24);
+                __syncwarp();
+                const uint32_t w0 = scr[5 * (4 * rg) + cg], w1 = scr[5 * (4 * rg + 1) + cg];
+                const uint32_t w2 = scr[5 * (4 * rg + 2) + cg], w3 = scr[5 * (4 * rg + 3) + cg];
+                const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
+                                 __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+                if (rows4_ok) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const uint32_t col = col0 + 16 * (ch0 + c) + 4 * cg + jj;
+                        if (col < args.rowsB) {
+                            if constexpr (RMW) {
+                                uint32_t ax;
+                                o[jj] = combine_word(rc, o[jj], old[4 * c + jj], ax, m);
+                                if (rc == RC_KARATSUBA_F) *reinterpret_cast<uint32_t *>(aux4 + (size_t)col * args.ldc8u) = ax;
+                            }
+                            *reinterpret_cast<uint32_t *>(out4 + (size_t)col * args.ldc8u) = o[jj];
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(acc), 0));   // tell the leader: this warp has drained the buffer
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();          // nobody frees tensor memory while the peer may still use the pair's resources
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CUDA-core cross-check (debug flag GEMMUL8_FLAG_GEMM_SIMT): one thread per C element, dp4a.
 // ---------------------------------------------------------------------------------------------
@@ -613,7 +865,7 @@ cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, BLOCK_N)) return cudaErrorInvalidValue;
     const char *dbg = getenv("OZ_DEBUG_SCHED");   // tuning knob: "tile" forces the tile-major schedule, "skipcrt" idles the CRT warps
     KernelArgs a = make_args(p, EPI == EPI_CRT || (dbg && strstr(dbg, "tile")));
-    a.debug_skip_crt = (dbg && strstr(dbg, "skipcrt")) ? 1 : 0;
+    a.debug_skip_crt = (dbg && strstr(dbg, "skipcrt")) ? 1 : (dbg && strstr(dbg, "halfb")) ? 2 : 0;
     auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT, RMW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return e;
@@ -632,12 +884,49 @@ cudaError_t launch_simt_t(const GemmProblem &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// CTA-pair kernel for EPI_RESIDUE (all combine modes): opt-in with OZ_GEMM_PAIR=1.  It is bit-identical
+// (tests/test_parity_gpu.py::test_cta_pair_kernel) and pulls 33 % fewer operand bytes through L2, but its L2 hit rate
+// collapses (47 % vs 88 %, DRAM reads 247 GB vs 38 GB per call at 16384^3: profiles/r01_pair_kernel_notes.md), and with
+// HBM that busy the power-capped clock falls: 46.6 - 54.8 ms against 43.6 ms for the single-CTA kernel.
+bool pair_kernel_enabled() {
+    const char *e = getenv("OZ_GEMM_PAIR");
+    return e && e[0] == '1' && sm_count() >= 2;
+}
+template <bool RMW>
+cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, 128)) return cudaErrorInvalidValue;
+    if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, 128)) return cudaErrorInvalidValue;
+    PairArgs a{};
+    a.rowsA = (uint32_t)p.rowsA; a.rowsB = (uint32_t)p.rowsB;
+    a.num_kb = (uint32_t)((p.ld8i + BLOCK_K - 1) / BLOCK_K);
+    a.first_modulus = p.first_modulus;
+    a.rows_store = (uint32_t)((p.rowsA + 3) / 4 * 4);
+    const char *be = getenv("OZ_PAIR_BAND");
+    a.sched.init((uint32_t)((p.rowsA + 255) / 256), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N), p.num_slices,
+                 be ? (uint32_t)atoi(be) : (uint32_t)PAIR_BAND);
+    a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
+    a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
+    const char *sk = getenv("OZ_PAIR_SKEW");
+    a.debug_skew = sk ? (uint32_t)atoi(sk) : 0u;
+    auto kern = oz_gemm_pair_kernel<RMW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    const uint32_t max_pairs = (uint32_t)sm_count() / 2;
+    const uint32_t pairs = a.sched.total < max_pairs ? a.sched.total : max_pairs;
+    kern<<<2 * pairs, NUM_THREADS, PAIR_SMEM_TOTAL, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStream_t st) {
     if (p.rowsA == 0 || p.rowsB == 0 || p.num_slices == 0) return cudaSuccess;
     switch (epi) {
-        case EPI_RESIDUE: return p.combine == RC_STORE ? launch_tc<EPI_RESIDUE>(p, st) : launch_tc<EPI_RESIDUE, double, false, true>(p, st);
+        case EPI_RESIDUE:
+            if (pair_kernel_enabled()) return p.combine == RC_STORE ? launch_pair<false>(p, st) : launch_pair<true>(p, st);
+            return p.combine == RC_STORE ? launch_tc<EPI_RESIDUE>(p, st) : launch_tc<EPI_RESIDUE, double, false, true>(p, st);
         case EPI_INT32:   return launch_tc<EPI_INT32>(p, st);
         case EPI_ABSMAX:  return launch_tc<EPI_ABSMAX>(p, st);
         case EPI_CRT:

@@ -231,6 +231,32 @@ def test_two_call_split_equals_single_call(g):
     assert torch.equal(w["A8i"][:, :m], v["A8i"][:, :m]) and torch.equal(w["B8i"], v["B8i"]) and torch.equal(C2, C)
 
 
+def test_cta_pair_kernel(g, monkeypatch):
+    """The opt-in cta_group::2 kernel (two CTAs share a 256 x 256 tile, OZ_GEMM_PAIR=1): bit-identical residues and C,
+    ragged shapes included, and through the complex combine passes."""
+    torch = torch_()
+    for (m, n, k, N) in [(777, 1301, 900, 14), (300, 200, 4096, 8), (129, 257, 130, 20)]:
+        A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=5)
+        monkeypatch.setenv("OZ_GEMM_PAIR", "0")
+        C, v = run_ours(g, m, n, k, N, True, A, B)
+        monkeypatch.setenv("OZ_GEMM_PAIR", "1")
+        Cp, vp = run_ours(g, m, n, k, N, True, A, B)
+        assert torch.equal(v["C8u"][:, :, :m], vp["C8u"][:, :, :m]) and torch.equal(C, Cp)
+    m, n, k, N = 333, 222, 444, 13
+    Az = g.phi_matrix(m, k, 0.5, torch.complex128, seed=1)
+    Bz = g.phi_matrix(k, n, 0.5, torch.complex128, seed=2)
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("OZ_GEMM_PAIR", pair)
+        Cz = torch.zeros((n, m), dtype=torch.complex128, device="cuda")
+        work = torch.zeros(g.workSize(m, n, k, N, g.COMPLEX_KARATSUBA_MULT), dtype=torch.uint8, device="cuda")
+        g.gemm(None, 0, 0, m, n, k, 1.0, Az, m, Bz, k, 0.0, Cz, m, N, True, work, computeType=g.COMPLEX_KARATSUBA_MULT)
+        torch.cuda.synchronize()
+        outs.append(Cz)
+    monkeypatch.delenv("OZ_GEMM_PAIR", raising=False)
+    assert torch.equal(torch.view_as_real(outs[0]), torch.view_as_real(outs[1]))
+
+
 def test_strip_pipeline_equals_default(g):
     """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
     torch = torch_()

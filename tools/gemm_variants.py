@@ -12,7 +12,8 @@ B = g.phi_matrix(k, n, 0.5, torch.float64)
 work = torch.empty(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
 C = torch.zeros((n, m), dtype=torch.float64, device="cuda")
 
-def run(name, flags, env):
+def run(name, flags, env, pair=False):
+    os.environ["OZ_GEMM_PAIR"] = "1" if pair else "0"
     if env is None:
         os.environ.pop("OZ_DEBUG_SCHED", None)
     else:
@@ -31,8 +32,10 @@ def run(name, flags, env):
     print(json.dumps({"variant": name, "total_ms": e0.elapsed_time(e1) / reps, "phases_ms_in_series": [p / 1e6 for p in ph]}), flush=True)
 
 for rep in range(2):
-    run("default: phases in series (item-major GEMM + crt kernel)", 0, None)
+    run("default: single-CTA GEMM (cta_group::1), phases in series", 0, None)
+    run("CTA-pair GEMM (cta_group::2), phases in series", 0, None, pair=True)
     run("column-strip pipeline on 3 streams", g.FLAG_STRIPS, None)
-    run("in series, tile-major", 0, "tile")
+    run("EXPERIMENT (wrong results): single-CTA, B tile loaded every other k-block only", 0, "halfb", pair=False)
+    run("single-CTA, tile-major", 0, "tile", pair=False)
     run("fused", g.FLAG_FUSED_CRT, None)
     run("fused skipcrt", g.FLAG_FUSED_CRT, "skipcrt")

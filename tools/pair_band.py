@@ -1,0 +1,20 @@
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gemmul8_b200 as g
+m = n = k = 16384; N = 14
+A = g.phi_matrix(m, k, 0.5, torch.float64); B = g.phi_matrix(k, n, 0.5, torch.float64)
+work = torch.empty(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+C = torch.zeros((n, m), dtype=torch.float64, device="cuda")
+def run(tag):
+    for _ in range(2): g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work)
+    torch.cuda.synchronize()
+    t = [0.0]*4
+    for _ in range(4):
+        x = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=g.FLAG_TIMERS)
+        t = [a+b for a, b in zip(t, x)]
+    print(tag, "gemm ms %.2f" % (t[1]/4/1e6), flush=True)
+os.environ["OZ_GEMM_PAIR"] = "0"; run("single")
+os.environ["OZ_GEMM_PAIR"] = "1"
+for b, sk in ((8, 0), (16, 0), (8, 500), (8, 2000), (8, 8000), (16, 500), (16, 2000), (16, 8000)):
+    os.environ["OZ_PAIR_BAND"] = str(b); os.environ["OZ_PAIR_SKEW"] = str(sk); run("pair band %d skew %d ns/pair" % (b, sk))
