@@ -140,22 +140,22 @@ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 struct Sched {
-    uint32_t tiles_m, tiles_n, slices, full_bands, per_band_full, total;
-    __host__ __device__ void init(uint32_t tm, uint32_t tn, uint32_t s) {
-        tiles_m = tm; tiles_n = tn; slices = s;
-        full_bands = tm / BAND_M;
-        per_band_full = BAND_M * tn * s;
+    uint32_t tiles_m, tiles_n, slices, full_bands, per_band_full, total, band_m;
+    __host__ __device__ void init(uint32_t tm, uint32_t tn, uint32_t s, uint32_t band = BAND_M) {
+        tiles_m = tm; tiles_n = tn; slices = s; band_m = band;
+        full_bands = tm / band_m;
+        per_band_full = band_m * tn * s;
         total = tm * tn * s;
     }
     __device__ __forceinline__ void decode(uint32_t item, uint32_t &tm, uint32_t &tn, uint32_t &j) const {
         uint32_t band = item / per_band_full, rem, bm;
-        if (band < full_bands) { rem = item - band * per_band_full; bm = BAND_M; }
-        else { band = full_bands; rem = item - full_bands * per_band_full; bm = tiles_m - full_bands * BAND_M; }
+        if (band < full_bands) { rem = item - band * per_band_full; bm = band_m; }
+        else { band = full_bands; rem = item - full_bands * per_band_full; bm = tiles_m - full_bands * band_m; }
         const uint32_t per_j = bm * tiles_n;
         j = rem / per_j;
         const uint32_t r2 = rem - j * per_j;
         tn = r2 / bm;
-        tm = band * BAND_M + (r2 - tn * bm);
+        tm = band * band_m + (r2 - tn * bm);
     }
 };
 
@@ -836,8 +836,9 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     a.first_modulus = p.first_modulus;
     a.num_slices = p.num_slices;
     a.tile_major = tile_major ? 1u : 0u;
+    const char *be = getenv("OZ_BAND");   // tuning knob: row tiles per scheduling band
     a.sched.init((uint32_t)((p.rowsA + BLOCK_M - 1) / BLOCK_M), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N),
-                 tile_major ? 1u : p.num_slices);
+                 tile_major ? 1u : p.num_slices, be ? (uint32_t)atoi(be) : (uint32_t)BAND_M);
     a.C = p.C; a.ldc = p.ldc; a.sftA = p.sftA; a.sftB = p.sftB; a.alpha = p.alpha; a.beta = p.beta;
     a.ab_mode = alpha_beta_mode(p.alpha, p.beta);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;

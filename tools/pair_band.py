@@ -14,7 +14,7 @@ def run(tag):
         x = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=g.FLAG_TIMERS)
         t = [a+b for a, b in zip(t, x)]
     print(tag, "gemm ms %.2f" % (t[1]/4/1e6), flush=True)
-os.environ["OZ_GEMM_PAIR"] = "0"; run("single")
-os.environ["OZ_GEMM_PAIR"] = "1"
-for b, sk in ((8, 0), (16, 0), (8, 500), (8, 2000), (8, 8000), (16, 500), (16, 2000), (16, 8000)):
-    os.environ["OZ_PAIR_BAND"] = str(b); os.environ["OZ_PAIR_SKEW"] = str(sk); run("pair band %d skew %d ns/pair" % (b, sk))
+os.environ["OZ_GEMM_PAIR"] = "0"
+for rep in range(2):
+    for b in (8, 12, 16, 24, 32, 48, 64, 128):
+        os.environ["OZ_BAND"] = str(b); run("single-CTA band %d" % b)
