@@ -1,6 +1,7 @@
 """Build the in-tree shared libraries with nvcc for sm_100a (cross-compiles without a GPU).
 
   libgemmul8_b200.so        product: C ABI (include/gemmul8_b200.h), kernels, no cuBLAS dependency
+  libgemmul8_b200_blas.so   LD_PRELOAD interposer: cublasDgemm / Sgemm / Zgemm / Cgemm / GemmEx -> the product library
   libgemmul8_b200_aux.so    measurement helpers used by tests / bench only (phi-matrix generator,
                             double-double truth GEMM, cuBLAS native baselines)
 """
@@ -13,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgemmul8_b200.so")
 AUX = os.path.join(HERE, "libgemmul8_b200_aux.so")
+BLAS = os.path.join(HERE, "libgemmul8_b200_blas.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -47,6 +49,12 @@ def build(force=False, verbose=False):
     if force or _stale(LIB, deps):
         extra = ["-Xptxas", "-v"] if verbose else []
         out += _run([nvcc(), *ARCH, *COMMON, *extra, "-shared", "-o", LIB, *core, "-ldl"])
+    blas_src = os.path.join(CSRC, "oz_interpose.cpp")
+    if os.path.exists(blas_src) and (force or _stale(BLAS, [blas_src, LIB])):
+        # host code only (g++); resolved against the product library at load time, cuBLAS itself through RTLD_NEXT
+        cuda = os.path.dirname(os.path.dirname(nvcc()))
+        out += _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(cuda, "include"), "-o", BLAS, blas_src,
+                     "-L", HERE, "-lgemmul8_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-ldl", "-Wl,-rpath,$ORIGIN"])
     aux_src = os.path.join(CSRC, "oz_aux.cu")
     if os.path.exists(aux_src) and (force or _stale(AUX, [aux_src])):
         out += _run([nvcc(), *ARCH, *COMMON, "-shared", "-o", AUX, aux_src, "-lcublas"])
