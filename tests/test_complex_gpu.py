@@ -179,3 +179,42 @@ def test_real_types_reject_complex_compute_type_and_vice_versa(g, capfd):
     t = g.gemm(None, 0, 0, 8, 8, 8, 1.0, A, 8, A, 8, 0.0, C, 8, 4, True, work, computeType=g.REAL_DEFAULT)
     assert t == [0.0] * 4 and (C == 5.0).all()
     assert "Unsupported compute type" in capfd.readouterr().err
+
+
+def test_no_writes_outside_workspace_and_c(g, monkeypatch):
+    """compute-sanitizer is not available on this pool: guard bands of 4 KiB around `work` and around C, filled
+    with a sentinel, must survive every kernel family (real fast / accurate, the three complex modes, ragged
+    shapes, the opt-in CTA-pair and fused-CRT kernels)."""
+    torch = torch_()
+    G = 4096
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * G + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = (-buf.data_ptr()) % 16 + G          # keep the 16-byte alignment the API asks for
+        off += (-(buf.data_ptr() + off)) % 16
+        return buf, buf[off:off + nbytes], off
+
+    def check(buf, off, nbytes, what):
+        assert (buf[:off] == 0xA5).all() and (buf[off + nbytes:] == 0xA5).all(), what
+
+    cases = [(301, 203, 262, 14, True, 0, 0, torch.float64, 0, 0), (129, 257, 131, 20, False, 1, 1, torch.float64, 0, 0),
+             (77, 45, 33, 6, True, 0, 1, torch.float32, 0, 0), (640, 520, 300, 14, True, 0, 0, torch.float64, 0, g.FLAG_FUSED_CRT)]
+    for ct in (BIG, CLASSIC, KARA):
+        cases += [(131, 70, 101, 9, True, 0, 2, torch.complex128, ct, 0), (70, 53, 100, 8, False, 1, 0, torch.complex64, ct, 0)]
+    for pair in ("0", "1"):
+        monkeypatch.setenv("OZ_GEMM_PAIR", pair)
+        for (m, n, k, N, fast, opA, opB, dt, ct, flags) in cases:
+            A, B = operands(g, m, n, k, opA, opB, dt, dt)
+            ws = g.workSize(m, n, k, N, ct)
+            wbuf, work, woff = guarded(ws)
+            work.zero_()
+            es = torch.empty(0, dtype=dt).element_size()
+            cbuf, cbytes, coff = guarded(m * n * es)
+            C = cbytes.view(dt).view(n, m)
+            C.zero_()
+            g.gemm(None, opA, opB, m, n, k, 1.0, A, A.shape[1], B, B.shape[1], 0.0, C, m, N, fast, work, computeType=ct, flags=flags)
+            torch.cuda.synchronize()
+            check(wbuf, woff, ws, ("work", m, n, k, N, ct, pair))
+            check(cbuf, coff, m * n * es, ("C", m, n, k, N, ct, pair))
+            assert torch.isfinite(torch.view_as_real(C) if C.is_complex() else C).all()
+    monkeypatch.delenv("OZ_GEMM_PAIR", raising=False)
