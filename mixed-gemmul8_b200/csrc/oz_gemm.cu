@@ -39,6 +39,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <cudaTypedefs.h>
 
 namespace oz {
@@ -171,17 +172,27 @@ struct KernelArgs {
     void *C; size_t ldc;
     const int16_t *sftA; const int16_t *sftB;
     double alpha, beta; int ab_mode; int debug_skip_crt;
+    uint32_t cta_map, num_sms;
 };
 
 // the it-th work item of this CTA; false when the CTA has run out of work
+__device__ __forceinline__ uint32_t virtual_cta(const KernelArgs &a) {
+    if (a.cta_map == 0 || gridDim.x != a.num_sms) return blockIdx.x;   // experiment knob OZ_MAP: work by SM id instead of block id
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (a.cta_map == 1) return smid;
+    if (a.cta_map == 2) return (smid & 1u) * (a.num_sms / 2) + (smid >> 1);       // TPC siblings far apart
+    return (smid % 8u) * ((a.num_sms + 7) / 8) + smid / 8u < a.num_sms ? (smid % 8u) * ((a.num_sms + 7) / 8) + smid / 8u : smid;
+}
 __device__ __forceinline__ bool next_work(const KernelArgs &a, uint32_t it, uint32_t &tm, uint32_t &tn, uint32_t &j) {
     uint32_t unit, jj = 0;
+    const uint32_t vb = virtual_cta(a);
     if (a.tile_major) {
         const uint32_t t = it / a.num_slices;
         jj   = it - t * a.num_slices;
-        unit = blockIdx.x + t * gridDim.x;
+        unit = vb + t * gridDim.x;
     } else {
-        unit = blockIdx.x + it * gridDim.x;
+        unit = vb + it * gridDim.x;
     }
     if (unit >= a.sched.total) return false;
     a.sched.decode(unit, tm, tn, j);
@@ -530,8 +541,8 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 // a 256 x 256 tile.  Each CTA keeps its own 128 rows of A and HALF of the B tile (128 columns) in
 // shared memory; the tensor cores of the pair exchange the B halves, so per 256 x 256 x 128 block of
 // MACs the pair pulls 64 KB through L2 instead of the 96 KB two independent CTAs need.  The kernel
-// is power-bound on B200; whether the saved L2 traffic turns into clock is measured in DESIGN.md 3.4
-// (so far it does not: the variant is opt-in).
+// is power-bound on B200, and the saved traffic turns into clock -- PROVIDED the pairs are placed like
+// the CTAs of a plain launch (see `placement_slots`): DESIGN.md 3.4.
 //   every CTA    warp 0 : TMA producer of its own A rows and B half; the bytes are accounted on the
 //                         LEADER's full barrier (cp.async.bulk.tensor .cta_group::2)
 //   leader only  warp 1 : issues tcgen05.mma.cta_group::2 (M 256, N 256, K 32); its commits are
@@ -608,6 +619,7 @@ struct PairArgs {
     uint8_t *C8u; size_t ldc8u, sizeC;
     int combine; uint8_t *C8u_aux;
     uint32_t debug_skew;
+    const uint32_t *slot;   // smid -> block index of a plain launch (nullptr: use blockIdx)
 };
 
 template <bool RMW>
@@ -625,7 +637,17 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank    = cluster_ctarank();         // 0 = leader
-    const uint32_t pair    = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    // Work goes by PLACEMENT, not by block index: a cluster launch fills the SMs GPC by GPC, which would put all pairs
+    // that share a B panel behind one GPC port (measured: +5 ms from that alone).  slot[smid] is the block index a plain
+    // launch gives this SM (TPC by TPC, round-robin over the GPCs), so the sharers end up spread exactly as in the
+    // single-CTA kernel.
+    uint32_t pair = blockIdx.x >> 1;
+    if (args.slot != nullptr) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        pair = args.slot[smid] >> 1;
+    }
+    const uint32_t npairs = gridDim.x >> 1;
     const uint32_t num_kb  = args.num_kb;
     const uint32_t total   = args.sched.total;
 
@@ -867,10 +889,25 @@ cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     const char *dbg = getenv("OZ_DEBUG_SCHED");   // tuning knob: "tile" forces the tile-major schedule, "skipcrt" idles the CRT warps
     KernelArgs a = make_args(p, EPI == EPI_CRT || (dbg && strstr(dbg, "tile")));
     a.debug_skip_crt = (dbg && strstr(dbg, "skipcrt")) ? 1 : (dbg && strstr(dbg, "halfb")) ? 2 : 0;
+    const char *mp = getenv("OZ_MAP");
+    a.cta_map = mp ? (uint32_t)atoi(mp) : 0u;
+    a.num_sms = (uint32_t)sm_count();
     auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT, RMW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
+    const char *cl = getenv("OZ_CLUSTER");   // experiment: the same kernel launched as clusters of 2 (placement effect on L2)
+    if (cl && atoi(cl) == 2 && grid % 2 == 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_TOTAL; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, a);
+        count_launch();
+        return le != cudaSuccess ? le : cudaGetLastError();
+    }
     kern<<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(ma, mb, a);
     count_launch();
     return cudaGetLastError();
@@ -885,13 +922,50 @@ cudaError_t launch_simt_t(const GemmProblem &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// CTA-pair kernel for EPI_RESIDUE (all combine modes): opt-in with OZ_GEMM_PAIR=1.  It is bit-identical
-// (tests/test_parity_gpu.py::test_cta_pair_kernel) and pulls 33 % fewer operand bytes through L2, but its L2 hit rate
-// collapses (47 % vs 88 %, DRAM reads 247 GB vs 38 GB per call at 16384^3: profiles/r01_pair_kernel_notes.md), and with
-// HBM that busy the power-capped clock falls: 46.6 - 54.8 ms against 43.6 ms for the single-CTA kernel.
+
+// ---------------------------------------------------------------------------------------------
+// placement probe: which block index does a plain 1-CTA-per-SM launch give each SM?
+// ---------------------------------------------------------------------------------------------
+__global__ void placement_probe_kernel(uint32_t *slot) {
+    extern __shared__ uint8_t probe_smem[];
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x == 0) slot[smid] = blockIdx.x;
+    probe_smem[threadIdx.x] = 1;       // the big dynamic allocation keeps it at one CTA per SM
+    __nanosleep(200000);               // ... and every CTA resident at the same time
+}
+const uint32_t *placement_slots() {     // nullptr if the probe did not produce a permutation (busy GPU, MIG, ...)
+    static const uint32_t *table = nullptr;
+    static bool tried = false;
+    if (tried) return table;
+    tried = true;
+    const int n = sm_count();
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, sizeof(uint32_t) * (size_t)n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaDeviceSynchronize();
+    cudaMemset(d, 0xff, sizeof(uint32_t) * (size_t)n);
+    cudaFuncSetAttribute(placement_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    placement_probe_kernel<<<n, 32, 200 * 1024>>>(d);
+    std::vector<uint32_t> h((size_t)n), seen((size_t)n, 0);
+    if (cudaMemcpy(h.data(), d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    bool ok = true;
+    for (int i = 0; i < n; ++i) { if (h[i] >= (uint32_t)n || seen[h[i]]++) ok = false; }
+    for (int i = 0; i + 1 < n; i += 2) ok = ok && (h[i] >> 1) == (h[i + 1] >> 1);   // TPC siblings hold consecutive blocks
+    if (!ok) { cudaFree(d); return nullptr; }
+    table = d;                          // lives as long as the process
+    return table;
+}
+
+// CTA-pair kernel for EPI_RESIDUE (all combine modes).  Default whenever the placement table exists (whole GPU, even SM
+// count); OZ_GEMM_PAIR=0 selects the single-CTA kernel, OZ_GEMM_PAIR=1 forces the pair kernel even without the table.
+// Measured at 16384^3, 14 moduli, same box: single-CTA 46.7 / 48.7 ms, pairs placed by block index 53.9 - 57.2 ms,
+// pairs placed like a plain launch 44.7 / 45.2 ms (profiles/r01_pair_kernel_notes.md).
 bool pair_kernel_enabled() {
     const char *e = getenv("OZ_GEMM_PAIR");
-    return e && e[0] == '1' && sm_count() >= 2;
+    if (e && e[0] == '0') return false;
+    if (sm_count() < 2 || (sm_count() & 1)) return false;
+    if (e && e[0] == '1') return true;
+    return placement_slots() != nullptr;
 }
 template <bool RMW>
 cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
@@ -915,6 +989,8 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const uint32_t max_pairs = (uint32_t)sm_count() / 2;
     const uint32_t pairs = a.sched.total < max_pairs ? a.sched.total : max_pairs;
+    const char *pm = getenv("OZ_PAIR_MAP");
+    a.slot = (pairs == max_pairs && (uint32_t)sm_count() == 2 * max_pairs && !(pm && pm[0] == '0')) ? placement_slots() : nullptr;
     kern<<<2 * pairs, NUM_THREADS, PAIR_SMEM_TOTAL, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
     count_launch();
     return cudaGetLastError();

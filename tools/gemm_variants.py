@@ -13,7 +13,7 @@ work = torch.empty(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
 C = torch.zeros((n, m), dtype=torch.float64, device="cuda")
 
 def run(name, flags, env, pair=False):
-    os.environ["OZ_GEMM_PAIR"] = "1" if pair else "0"
+    os.environ["OZ_GEMM_PAIR"] = "" if pair else "0"
     if env is None:
         os.environ.pop("OZ_DEBUG_SCHED", None)
     else:
@@ -21,7 +21,7 @@ def run(name, flags, env, pair=False):
     for _ in range(3):
         g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=flags)
     torch.cuda.synchronize()
-    reps = 8
+    reps = 12
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -32,8 +32,8 @@ def run(name, flags, env, pair=False):
     print(json.dumps({"variant": name, "total_ms": e0.elapsed_time(e1) / reps, "phases_ms_in_series": [p / 1e6 for p in ph]}), flush=True)
 
 for rep in range(2):
-    run("default: single-CTA GEMM (cta_group::1), phases in series", 0, None)
-    run("CTA-pair GEMM (cta_group::2), phases in series", 0, None, pair=True)
+    run("default: CTA-pair GEMM (cta_group::2, pairs placed like a plain launch), phases in series", 0, None, pair=True)
+    run("single-CTA GEMM (cta_group::1), phases in series", 0, None)
     run("column-strip pipeline on 3 streams", g.FLAG_STRIPS, None)
     run("EXPERIMENT (wrong results): single-CTA, B tile loaded every other k-block only", 0, "halfb", pair=False)
     run("single-CTA, tile-major", 0, "tile", pair=False)

@@ -14,7 +14,11 @@ def run(tag):
         x = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=g.FLAG_TIMERS)
         t = [a+b for a, b in zip(t, x)]
     print(tag, "gemm ms %.2f" % (t[1]/4/1e6), flush=True)
-os.environ["OZ_GEMM_PAIR"] = "0"
+os.environ.pop("OZ_CLUSTER", None); os.environ.pop("OZ_MAP", None)
 for rep in range(2):
-    for b in (8, 12, 16, 24, 32, 48, 64, 128):
-        os.environ["OZ_BAND"] = str(b); run("single-CTA band %d" % b)
+    os.environ["OZ_GEMM_PAIR"] = "0"; run("single-CTA kernel")
+    os.environ["OZ_GEMM_PAIR"] = "1"
+    for b in (8, 16):
+        os.environ["OZ_PAIR_BAND"] = str(b)
+        os.environ["OZ_PAIR_MAP"] = "0"; run("pair kernel band %d, work by block index" % b)
+        os.environ["OZ_PAIR_MAP"] = "1"; run("pair kernel band %d, work by placement" % b)
