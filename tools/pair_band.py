@@ -15,10 +15,7 @@ def run(tag):
         t = [a+b for a, b in zip(t, x)]
     print(tag, "gemm ms %.2f" % (t[1]/4/1e6), flush=True)
 os.environ.pop("OZ_CLUSTER", None); os.environ.pop("OZ_MAP", None)
+os.environ["OZ_GEMM_PAIR"] = "1"; os.environ["OZ_PAIR_MAP"] = "1"
 for rep in range(2):
-    os.environ["OZ_GEMM_PAIR"] = "0"; run("single-CTA kernel")
-    os.environ["OZ_GEMM_PAIR"] = "1"
-    for b in (8, 16):
-        os.environ["OZ_PAIR_BAND"] = str(b)
-        os.environ["OZ_PAIR_MAP"] = "0"; run("pair kernel band %d, work by block index" % b)
-        os.environ["OZ_PAIR_MAP"] = "1"; run("pair kernel band %d, work by placement" % b)
+    for b in (2, 4, 6, 8, 10, 12, 16):
+        os.environ["OZ_PAIR_BAND"] = str(b); run("placed pair kernel, band %d" % b)
