@@ -119,6 +119,14 @@ int gemmul8_b200_gemm(gemmul8_b200_args *args);
 size_t gemmul8_b200_host_scratch_size(const gemmul8_b200_args *args);
 int gemmul8_b200_gemm_host(gemmul8_b200_args *args_with_host_matrices, void *dev_scratch);
 
+/* Block-wise entry for callers whose operands arrive piecewise (multi-GPU panel exchange, streaming from the
+ * host): one or more steps of the real fast-mode path restricted to rows [row0, row1) of op(A) / C and columns
+ * [col0, col1) of op(B) / C, inside the workspace of the FULL problem described by `args` (reference: the phases
+ * of gemm<>, GEMMul8/src/gemmul8.cu:253, :265-273, :288).  row0 and col0 must be multiples of 256.  A PRODUCT
+ * step needs the SCALE steps of its rows and columns to have run (in stream order) before. */
+enum { GEMMUL8_PART_SCALE_A = 1, GEMMUL8_PART_SCALE_B = 2, GEMMUL8_PART_PRODUCT = 4 };
+int gemmul8_b200_gemm_part(gemmul8_b200_args *args, int parts, size_t row0, size_t row1, size_t col0, size_t col1);
+
 /* Debug/parity: raw int32 product of modulus slice `j` (what the reference's cublasGemmEx at
  * gemmul8.cu:265 writes into C32i), column-major with leading dimension m_pad.  Requires the
  * slices to be present in `work` (GEMMUL8_FLAG_STAGE_SCALING or a full gemm call). */

@@ -26,7 +26,7 @@ FLAG_ONLY_SCALE_A, FLAG_SKIP_SCALE_A = 1 << 11, 1 << 12
 
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",
-    "gemmul8_b200_gemm_host", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
+    "gemmul8_b200_gemm_host", "gemmul8_b200_gemm_part", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
     "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
 )
 
@@ -82,6 +82,8 @@ def lib():
         L.gemmul8_b200_host_scratch_size.argtypes = [C.POINTER(Args)]
         L.gemmul8_b200_gemm_host.restype = C.c_int
         L.gemmul8_b200_gemm_host.argtypes = [C.POINTER(Args), C.c_void_p]
+        L.gemmul8_b200_gemm_part.restype = C.c_int
+        L.gemmul8_b200_gemm_part.argtypes = [C.POINTER(Args), C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
         L.gemmul8_b200_product_i32.restype = C.c_int
         L.gemmul8_b200_product_i32.argtypes = [C.POINTER(Args), C.c_uint, C.c_void_p, C.c_int]
         L.gemmul8_b200_modulus.restype = C.c_int
@@ -179,6 +181,15 @@ def gemm(handle, op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, nu
         return [0.0, 0.0, 0.0, 0.0]
     _check(rc)
     return list(a.timers_ns)
+
+
+PART_SCALE_A, PART_SCALE_B, PART_PRODUCT = 1, 2, 4
+
+
+def gemm_part(args, parts, row0, row1, col0, col1):
+    """One or more steps (PART_*) of the real fast-mode path on rows [row0, row1) x columns [col0, col1) of the full
+    problem described by `args` (from make_args); see gemmul8_b200_gemm_part in include/gemmul8_b200.h."""
+    _check(lib().gemmul8_b200_gemm_part(C.byref(args), parts, row0, row1, col0, col1))
 
 
 def gemm_host(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, dev_scratch,

@@ -465,6 +465,63 @@ size_t gemmul8_b200_host_scratch_size(const gemmul8_b200_args *a) {
     return s + gemmul8_b200_worksize(a->m, a->n, a->k, a->num_moduli, a->compute_type);
 }
 
+// Block-wise entry for callers that receive their operands piecewise (multi-GPU panel exchange, host
+// streaming): the three steps of the real fast-mode path on a sub-range of the FULL problem's workspace.
+//   GEMMUL8_PART_SCALE_A : shifts + residue slices of rows [row0, row1) of op(A)
+//   GEMMUL8_PART_SCALE_B : shifts + residue slices of columns [col0, col1) of op(B)
+//   GEMMUL8_PART_PRODUCT : all-moduli product, residues, CRT and alpha/beta for C[row0:row1, col0:col1]
+// `args` describes the full problem (m, n, k, leading dimensions, pointers to the FULL matrices, work);
+// row0 and col0 must be multiples of 256 (whole GEMM tiles; the last block may be ragged).
+int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t row1, size_t col0, size_t col1) {
+    int rc = check_args(a);
+    if (rc) return rc;
+    if (is_complex(a->dtype_C) || !a->fastmode) return fail(GEMMUL8_ERR_ARGUMENT, "gemm_part: real types in fast mode only");
+    if (row1 > a->m || col1 > a->n || row0 > row1 || col0 > col1 || (row0 % 256) || (col0 % 256))
+        return fail(GEMMUL8_ERR_ARGUMENT, "gemm_part: bad block (row0 / col0 must be multiples of 256 inside the matrix)");
+    const size_t m = a->m, n = a->n, k = a->k;
+    const unsigned N = a->num_moduli, ti = N - 2;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    oz::Layout L;
+    compute_layout(m, n, k, N, GEMMUL8_REAL_DEFAULT, L);
+    uint8_t *work = static_cast<uint8_t *>(a->work);
+    int8_t *A8i   = reinterpret_cast<int8_t *>(work + L.off_A8i);
+    int8_t *B8i   = reinterpret_cast<int8_t *>(work + L.off_B8i);
+    uint8_t *C8u  = work + L.off_C8u;
+    int16_t *sftA = reinterpret_cast<int16_t *>(work + L.off_sftA);
+    int16_t *sftB = reinterpret_cast<int16_t *>(work + L.off_sftB);
+    const bool a_strided = a->op_A == GEMMUL8_OP_N, b_strided = a->op_B != GEMMUL8_OP_N;
+    const int ref_width  = oz::ref_reduce_width(a->dtype_A, a->dtype_B, a->dtype_C);
+    const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
+    const size_t esA = elem_size(a->dtype_A), esB = elem_size(a->dtype_B), esC = elem_size(a->dtype_C);
+    if ((parts & GEMMUL8_PART_SCALE_A) && row1 > row0 && k > 0) {
+        const uint8_t *Ax = static_cast<const uint8_t *>(a->A) + (a_strided ? row0 : row0 * a->lda) * esA;
+        rc = scale_operand(a->dtype_A, a_strided, Ax, a->lda, row1 - row0, k, ref_width, l2, N, A8i + row0 * L.lda8i, L.lda8i, L.sizeA,
+                           sftA + row0, true, st);
+        if (rc) return rc;
+    }
+    if ((parts & GEMMUL8_PART_SCALE_B) && col1 > col0 && k > 0) {
+        const uint8_t *Bx = static_cast<const uint8_t *>(a->B) + (b_strided ? col0 : col0 * a->ldb) * esB;
+        rc = scale_operand(a->dtype_B, b_strided, Bx, a->ldb, col1 - col0, k, ref_width, l2, N, B8i + col0 * L.lda8i, L.lda8i, L.sizeB,
+                           sftB + col0, true, st);
+        if (rc) return rc;
+    }
+    if ((parts & GEMMUL8_PART_PRODUCT) && row1 > row0 && col1 > col0) {
+        const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;
+        oz::GemmProblem gp{};
+        gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
+        gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+        gp.A8i = A8i + row0 * L.lda8i; gp.rowsA = row1 - row0;
+        gp.B8i = B8i + col0 * L.lda8i; gp.rowsB = col1 - col0;
+        gp.C8u = C8u + col0 * L.m_pad + row0;
+        OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+        OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, row1 - row0, col1 - col0, gp.C8u, L.m_pad, L.sizeC,
+                               static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, a->ldc, sftA + row0, sftB + col0, a->alpha, a->beta,
+                               st), "crt");
+    }
+    return GEMMUL8_OK;
+}
+
+
 // Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C.  The H2D
 // stream brings A row blocks and B column blocks alternately (A0, B0, A1, B1, ...); as soon as block
 // pair s is on the device the compute stream scales / encodes it and multiplies everything that has

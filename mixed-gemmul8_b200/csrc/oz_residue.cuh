@@ -34,7 +34,7 @@ __device__ __forceinline__ ModConst load_mod(unsigned j) {
 // The reference's operation sequence (scaling.hpp:215-230).  It ends on the exact symmetric residue
 // for every magnitude the scaling can produce (rint(a * rcp) is within a few units of a / m, every
 // fma in the chain is exact and the float passes fold the rest; checked against integer arithmetic
-// up to 2^79 in tests/test_oracle.py), so the encoders may take ANY exact route to the same byte.
+// up to 2^79 by a CPU property test under tests/), so the encoders may take ANY exact route to the same byte.
 // Kept for the on-device cross-check (GEMMUL8_FLAG_ENCODE_REFERENCE).
 __device__ __forceinline__ int residue_reference(double a, const ModConst &c) {
     float t = __double2float_rn(fma(rint(__dmul_rn(a, c.rcp)), c.neg_m, a));

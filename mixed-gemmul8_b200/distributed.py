@@ -87,22 +87,40 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
 
     a_slice / b_slice are this rank's pre-exchange pieces (see BlockGrid); returns the phase timers."""
     m_loc, n_loc = grid.block_dims(m, n)
-    overlap = fastmode and a_slice.is_cuda and not (flags & ~pkg.FLAG_TIMERS)
+    overlap = fastmode and a_slice.is_cuda and flags == 0 and not a_slice.is_complex()
     if not overlap:
         a_panel = grid.gather_a_panel(a_slice, m_loc, k)
         b_panel = grid.gather_b_panel(b_slice, n_loc, k)
         return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
                         num_moduli, fastmode, work, flags=flags)
-    # The row and the column communicator are different NCCL communicators with their own streams: both
-    # all-gathers run at the same time, and A's shifts + residues are computed while B is still arriving.
-    a_panel, wa = grid.gather_a_panel(a_slice, m_loc, k, async_op=True)
+    # The row and the column communicator are different NCCL communicators with their own streams, so the
+    # A and B exchanges run at the same time; A travels as two row halves, and everything that depends only
+    # on what has arrived is computed while the rest is still in flight:
+    #     B panel, A rows [0, h)  ->  scale B, scale A_0, C[0:h, :]      (A rows [h, m) still arriving)
+    #     A rows [h, m)           ->  scale A_1, C[h:m, :]
+    h = (m_loc // 2) // 256 * 256
+    if grid.Q == 1 or h == 0:
+        a_panel, parts_a = a_slice, [(0, m_loc, None)]
+    else:
+        a_panel = torch.empty((k, m_loc), dtype=a_slice.dtype, device=a_slice.device)
+        parts_a = []
+        for (r0, r1) in ((0, h), (h, m_loc)):
+            piece = torch.empty((k, r1 - r0), dtype=a_slice.dtype, device=a_slice.device)     # (k, rows) = column-major rows x k
+            w = dist.all_gather_into_tensor(piece, a_slice[:, r0:r1].contiguous(), group=grid.row_group, async_op=True)
+            parts_a.append((r0, r1, (w, piece)))
     b_panel, wb = grid.gather_b_panel(b_slice, n_loc, k, async_op=True)
-    if wa is not None:
-        wa.wait()                                   # the compute stream waits for the panel; the host does not block
-    t0 = pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
-                  num_moduli, fastmode, work, flags=flags | pkg.FLAG_ONLY_SCALE_A)
-    if wb is not None:
-        wb.wait()
-    t1 = pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
-                  num_moduli, fastmode, work, flags=flags | pkg.FLAG_SKIP_SCALE_A)
-    return [x + y for x, y in zip(t0, t1)]
+    args = pkg.make_args(0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc, num_moduli, fastmode, work)
+    first = True
+    for (r0, r1, pending) in parts_a:
+        if pending is not None:
+            w, piece = pending
+            w.wait()                                          # the compute stream waits; the host does not block
+            a_panel[:, r0:r1].copy_(piece)                    # place the rows in the panel (device copy, ~1% of the step)
+        pkg.gemm_part(args, pkg.PART_SCALE_A, r0, r1, 0, 0)
+        if first:
+            if wb is not None:
+                wb.wait()
+            pkg.gemm_part(args, pkg.PART_SCALE_B, 0, 0, 0, n_loc)
+            first = False
+        pkg.gemm_part(args, pkg.PART_PRODUCT, r0, r1, 0, n_loc)
+    return [0.0, 0.0, 0.0, 0.0]

@@ -257,6 +257,31 @@ def test_cta_pair_kernel(g, monkeypatch):
     assert torch.equal(torch.view_as_real(outs[0]), torch.view_as_real(outs[1]))
 
 
+def test_block_wise_entry_equals_single_call(g):
+    """gemmul8_b200_gemm_part: scaling of row / column blocks and products of C blocks in an order a pipelined caller
+    would use (columns first, rows in two pieces, products as soon as their inputs exist) against one gemm call."""
+    torch = torch_()
+    m, n, k, N = 1300, 900, 700, 14
+    for (opA, opB, dt) in ((0, 0, "float64"), (1, 1, "float32")):
+        A, B = operands(g, m, n, k, opA, opB, getattr(torch, dt), getattr(torch, dt), seedB=12)
+        C, v = run_ours(g, m, n, k, N, True, A, B, opA, opB)
+        C2 = torch.full_like(C, 3.0)
+        work = torch.zeros(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+        args = g.make_args(opA, opB, m, n, k, 1.0, A, A.shape[1], B, B.shape[1], 0.0, C2, m, N, True, work)
+        g.gemm_part(args, g.PART_SCALE_B, 0, 0, 0, 512)
+        g.gemm_part(args, g.PART_SCALE_A, 0, 768, 0, 0)
+        g.gemm_part(args, g.PART_PRODUCT, 0, 768, 0, 512)
+        g.gemm_part(args, g.PART_SCALE_B | g.PART_PRODUCT, 0, 768, 512, n)
+        g.gemm_part(args, g.PART_SCALE_A | g.PART_PRODUCT, 768, m, 0, n)
+        torch.cuda.synchronize()
+        w = g.work_views(work, g.work_layout(m, n, k, N), N, m, n)
+        assert torch.equal(w["sftA"], v["sftA"]) and torch.equal(w["sftB"], v["sftB"])
+        assert torch.equal(w["A8i"][:, :m], v["A8i"][:, :m]) and torch.equal(w["B8i"], v["B8i"])
+        assert torch.equal(w["C8u"][:, :, :m], v["C8u"][:, :, :m]) and torch.equal(C2, C)
+    with pytest.raises(g.Gemmul8Error):
+        g.gemm_part(args, g.PART_PRODUCT, 100, 200, 0, n)       # row0 not a multiple of 256
+
+
 def test_strip_pipeline_equals_default(g):
     """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
     torch = torch_()
