@@ -219,11 +219,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler.start()       # nvidia-smi needs a moment to come up: start it before the warm-up so the timed region is covered
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches0 = g.launch_count()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
