@@ -554,7 +554,7 @@ constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_SMEM_A = BLOCK_M * BLOCK_K;          // 128 rows of A
 constexpr int PAIR_SMEM_B = 128 * BLOCK_K;              // 128 of the tile's 256 columns of B
 constexpr int PAIR_STAGE  = PAIR_SMEM_A + PAIR_SMEM_B;  // 32 KiB per CTA and stage
-constexpr int PAIR_SMEM_TOTAL = PAIR_STAGES * PAIR_STAGE + SMEM_BARRIERS + SMEM_SCRATCH + 1024;
+constexpr int pair_smem_total(int stages) { return stages * PAIR_STAGE + SMEM_BARRIERS + SMEM_SCRATCH + 1024; }
 constexpr int PAIR_BAND = 8;                            // 256-row tiles per scheduling band
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -622,17 +622,17 @@ struct PairArgs {
     const uint32_t *slot;   // smid -> block index of a plain launch (nullptr: use blockIdx)
 };
 
-template <bool RMW>
+template <bool RMW, int NSTAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PairArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base  = smem_base + PAIR_STAGES * PAIR_STAGE;
+    const uint32_t bar_base  = smem_base + NSTAGES * PAIR_STAGE;
     auto full_bar   = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar  = [&](int s) { return bar_base + 8u * (PAIR_STAGES + s); };
-    auto tfull_bar  = [&](int s) { return bar_base + 8u * (2 * PAIR_STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * PAIR_STAGES + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * PAIR_STAGES + 4);
+    auto empty_bar  = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
+    auto tfull_bar  = [&](int s) { return bar_base + 8u * (2 * NSTAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGES + 4);
     uint32_t *tmem_slot_ptr  = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -656,7 +656,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }   // 8 epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -684,7 +684,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * PAIR_STAGE);   // both CTAs' bytes
                     tma_load_3d_pair(sa, &map_a, lbar, (int)(kb * BLOCK_K), rowA, (int)j);
                     tma_load_3d_pair(sa + PAIR_SMEM_A, &map_b, lbar, (int)(kb * BLOCK_K), rowB, (int)j);
-                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -707,7 +707,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                         umma_i8_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | (uint32_t)k) != 0 ? 1u : 0u);
                     tcgen05_commit_pair(empty_bar(stage));   // frees this stage in both CTAs
-                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
                 }
                 tcgen05_commit_pair(tfull_bar(acc));         // accumulator complete, both CTAs
             }
@@ -984,14 +984,17 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
     const char *sk = getenv("OZ_PAIR_SKEW");
     a.debug_skew = sk ? (uint32_t)atoi(sk) : 0u;
-    auto kern = oz_gemm_pair_kernel<RMW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_TOTAL);
+    const char *se = getenv("OZ_PAIR_STAGES");   // tuning knob
+    const int stages = se ? atoi(se) : PAIR_STAGES;
+    auto kern = stages == 4 ? oz_gemm_pair_kernel<RMW, 4> : stages == 5 ? oz_gemm_pair_kernel<RMW, 5> : oz_gemm_pair_kernel<RMW, 6>;
+    const int smem_bytes = pair_smem_total(stages == 4 ? 4 : stages == 5 ? 5 : 6);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const uint32_t max_pairs = (uint32_t)sm_count() / 2;
     const uint32_t pairs = a.sched.total < max_pairs ? a.sched.total : max_pairs;
     const char *pm = getenv("OZ_PAIR_MAP");
     a.slot = (pairs == max_pairs && (uint32_t)sm_count() == 2 * max_pairs && !(pm && pm[0] == '0')) ? placement_slots() : nullptr;
-    kern<<<2 * pairs, NUM_THREADS, PAIR_SMEM_TOTAL, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
+    kern<<<2 * pairs, NUM_THREADS, smem_bytes, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
     count_launch();
     return cudaGetLastError();
 }

@@ -16,6 +16,6 @@ def run(tag):
     print(tag, "gemm ms %.2f" % (t[1]/4/1e6), flush=True)
 os.environ.pop("OZ_CLUSTER", None); os.environ.pop("OZ_MAP", None)
 os.environ["OZ_GEMM_PAIR"] = "1"; os.environ["OZ_PAIR_MAP"] = "1"
-for rep in range(2):
-    for b in (2, 4, 6, 8, 10, 12, 16):
-        os.environ["OZ_PAIR_BAND"] = str(b); run("placed pair kernel, band %d" % b)
+for rep in range(3):
+    for st in (4, 5, 6):
+        os.environ["OZ_PAIR_STAGES"] = str(st); run("placed pair kernel, %d stages" % st)
