@@ -39,6 +39,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include <cudaTypedefs.h>
 
@@ -825,14 +826,14 @@ __global__ void oz_gemm_simt_kernel(const int8_t *__restrict__ A8i, const int8_t
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
+    static const PFN_cuTensorMapEncodeTiled_v12000 fn = [] {   // initialised once, thread-safe
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-    }
+            return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+        return (PFN_cuTensorMapEncodeTiled_v12000) nullptr;
+    }();
     return fn;
 }
 
@@ -871,13 +872,10 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     return a;
 }
 
-int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
+int sm_count() {   // of the current device
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
 }
 
@@ -934,12 +932,7 @@ __global__ void placement_probe_kernel(uint32_t *slot) {
     probe_smem[threadIdx.x] = 1;       // the big dynamic allocation keeps it at one CTA per SM
     __nanosleep(200000);               // ... and every CTA resident at the same time
 }
-const uint32_t *placement_slots() {     // nullptr if the probe did not produce a permutation (busy GPU, MIG, ...)
-    static const uint32_t *table = nullptr;
-    static bool tried = false;
-    if (tried) return table;
-    tried = true;
-    const int n = sm_count();
+const uint32_t *probe_placement(int n) {
     uint32_t *d = nullptr;
     if (cudaMalloc(&d, sizeof(uint32_t) * (size_t)n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     cudaDeviceSynchronize();
@@ -952,8 +945,21 @@ const uint32_t *placement_slots() {     // nullptr if the probe did not produce 
     for (int i = 0; i < n; ++i) { if (h[i] >= (uint32_t)n || seen[h[i]]++) ok = false; }
     for (int i = 0; i + 1 < n; i += 2) ok = ok && (h[i] >> 1) == (h[i + 1] >> 1);   // TPC siblings hold consecutive blocks
     if (!ok) { cudaFree(d); return nullptr; }
-    table = d;                          // lives as long as the process
-    return table;
+    return d;                           // lives as long as the process
+}
+// per device, probed once (thread-safe); nullptr if the probe did not produce a permutation (busy GPU, MIG, ...)
+const uint32_t *placement_slots() {
+    constexpr int kMaxDevices = 64;
+    static std::once_flag once[kMaxDevices];
+    static const uint32_t *table[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    std::call_once(once[dev], [dev] {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        table[dev] = n > 0 ? probe_placement(n) : nullptr;
+    });
+    return table[dev];
 }
 
 // CTA-pair kernel for EPI_RESIDUE (all combine modes).  Default whenever the placement table exists (whole GPU, even SM

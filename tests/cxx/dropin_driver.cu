@@ -48,6 +48,35 @@ static double run_case(cublasHandle_t handle, size_t m, size_t n, size_t k, unsi
     return err / scale;
 }
 
+// cuDoubleComplex through the three computeType_t values, against cublasZgemm
+static double run_complex(cublasHandle_t handle, gemmul8::computeType_t ct) {
+    const size_t m = 200, n = 160, k = 256;
+    const unsigned N = 14;
+    std::vector<cuDoubleComplex> hA(m * k), hB(k * n), c(m * n), cz(m * n);
+    std::vector<double> ra(2 * m * k), rb(2 * k * n);
+    fill(ra, 11); fill(rb, 12);
+    for (size_t i = 0; i < m * k; ++i) hA[i] = make_cuDoubleComplex(ra[2 * i], ra[2 * i + 1]);
+    for (size_t i = 0; i < k * n; ++i) hB[i] = make_cuDoubleComplex(rb[2 * i], rb[2 * i + 1]);
+    cuDoubleComplex *dA, *dB, *dC, *dZ;
+    void *work;
+    cudaMalloc(&dA, 16 * m * k); cudaMalloc(&dB, 16 * k * n); cudaMalloc(&dC, 16 * m * n); cudaMalloc(&dZ, 16 * m * n);
+    cudaMalloc(&work, gemmul8::workSize(m, n, k, N, ct));
+    cudaMemcpy(dA, hA.data(), 16 * m * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), 16 * k * n, cudaMemcpyHostToDevice);
+    const cuDoubleComplex one = make_cuDoubleComplex(1, 0), zero = make_cuDoubleComplex(0, 0);
+    gemmul8::gemm<gpuDoubleComplex>(handle, GPUBLAS_OP_N, GPUBLAS_OP_N, m, n, k, &one, dA, m, dB, k, &zero, dC, m, N, true, work, ct);
+    cublasZgemm(handle, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, (int)n, (int)k, &one, dA, (int)m, dB, (int)k, &zero, dZ, (int)m);
+    cudaMemcpy(c.data(), dC, 16 * m * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cz.data(), dZ, 16 * m * n, cudaMemcpyDeviceToHost);
+    double err = 0, scale = 0;
+    for (size_t i = 0; i < m * n; ++i) {
+        err = fmax(err, fmax(fabs(c[i].x - cz[i].x), fabs(c[i].y - cz[i].y)));
+        scale = fmax(scale, fmax(fabs(cz[i].x), fabs(cz[i].y)));
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dZ); cudaFree(work);
+    return err / scale;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "worksize")) {
         printf("%zu %zu\n", gemmul8::workSize(1024, 1024, 1024, 14),
@@ -63,7 +92,11 @@ int main(int argc, char **argv) {
     const double e_da = run_case<double, double, double>(handle, 300, 200, 400, 15, false);
     const double e_s  = run_case<float, float, float>(handle, 257, 129, 300, 7, true);
     const double e_m  = run_case<double, float, double>(handle, 128, 128, 256, 12, true);
-    printf("relerr dgemm-fast %.3e dgemm-accurate %.3e sgemm %.3e mixed %.3e\n", e_d, e_da, e_s, e_m);
+    const double e_zb = run_complex(handle, gemmul8::COMPLEX_BIG_MATRIX_ENCODE);
+    const double e_zc = run_complex(handle, gemmul8::COMPLEX_CLASSIC_MULT);
+    const double e_zk = run_complex(handle, gemmul8::COMPLEX_KARATSUBA_MULT);
+    printf("relerr dgemm-fast %.3e dgemm-accurate %.3e sgemm %.3e mixed %.3e zgemm big %.3e classic %.3e karatsuba %.3e\n", e_d, e_da, e_s,
+           e_m, e_zb, e_zc, e_zk);
     // unsupported computeType for real types: message on stderr, zero timers (GEMMul8/src/gemmul8.cu:174-177)
     double *dummy; void *work;
     cudaMalloc(&dummy, 8 * 64); cudaMalloc(&work, gemmul8::workSize(8, 8, 8, 4));
@@ -71,7 +104,7 @@ int main(int argc, char **argv) {
     std::vector<double> t = gemmul8::gemm<double>(handle, GPUBLAS_OP_N, GPUBLAS_OP_N, 8, 8, 8, &one, dummy, 8, dummy, 8, &zero, dummy, 8, 4,
                                                  true, work, gemmul8::COMPLEX_CLASSIC_MULT);
     const bool zeros = t.size() == 4 && t[0] == 0 && t[1] == 0 && t[2] == 0 && t[3] == 0;
-    const bool ok = e_d < 1e-12 && e_da < 1e-12 && e_s < 1e-5 && e_m < 1e-6 && zeros;
+    const bool ok = e_d < 1e-12 && e_da < 1e-12 && e_s < 1e-5 && e_m < 1e-6 && e_zb < 1e-12 && e_zc < 1e-12 && e_zk < 1e-12 && zeros;
     printf(ok ? "DROPIN OK\n" : "DROPIN FAILED\n");
     return ok ? 0 : 1;
 }

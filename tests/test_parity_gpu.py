@@ -282,6 +282,35 @@ def test_block_wise_entry_equals_single_call(g):
         g.gemm_part(args, g.PART_PRODUCT, 100, 200, 0, n)       # row0 not a multiple of 256
 
 
+def test_cuda_graph_capture_and_replay(g):
+    """The call is stream-ordered with no host synchronisation, allocation or constant upload (the reference does
+    2 + 4N device syncs and 2 cudaMemcpyToSymbol per call, gemmul8.cu:10-18, :236-241): it can be captured into a
+    CUDA graph and replayed on new data."""
+    torch = torch_()
+    m, n, k, N = 512, 768, 1024, 14
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=3)
+    work = torch.zeros(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+    C = torch.zeros((n, m), dtype=torch.float64, device="cuda")
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work)      # warm-up: one-time placement probe
+    torch.cuda.synchronize()
+    want1 = C.clone()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(graph, stream=s):
+        g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work)   # (uses the capturing stream)
+    C.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(C, want1)
+    A2 = g.phi_matrix(m, k, 1.0, torch.float64, seed=99)
+    want2, _ = run_ours(g, m, n, k, N, True, A2, B)
+    A.copy_(A2)                                                                  # new data, same graph
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(C, want2)
+
+
 def test_strip_pipeline_equals_default(g):
     """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
     torch = torch_()

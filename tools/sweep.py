@@ -116,6 +116,8 @@ def main():
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--csize", type=int, default=8192)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--csv", default=None, help="also write the rows in the reference's CSV format "
+                    "(oz2_results_*_time_*.csv: GEMMul8/testing/test_double.cu:204-213), one file, ours / reference / native rows")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     S, CS = a.size, a.csize
@@ -140,12 +142,36 @@ def main():
         cfgs.append(("z", "z", "z", CS, 14, True, 0.5, ct))
     cfgs.append(("z", "z", "z", CS, 14, False, 0.5, 3))
     cfgs.append(("c", "c", "c", CS, 6, True, 0.5, 3))
+    csv = open(a.csv, "w") if a.csv else None
+    if csv:
+        csv.write("phi,m,n,k,function,relerr_max,relerr_med,TFLOPS,total_time [sec],conv_64f_2_8i,cublasGemmEx,conv_32i_2_8u,inverse_scaling,\n")
+
+    def csv_rows(row):
+        if not csv or "error" in row:
+            return
+        pre = f"{row['phi']:e},{row['m']},{row['n']},{row['k']},"
+        tag = row["types"] + ("-" + row["computeType"] if row["computeType"] != "real" else "")
+        ph = row["phases_ms"]
+        csv.write(pre + f"{row['function']}[{tag}],{row['relerr_max']:e},{row['relerr_med']:e},{row['TFLOPS']:e},{row['total_time_ms'] / 1e3:e},"
+                        f"{ph['scaling'] / 1e3:e},{ph['int8_gemm_residues'] / 1e3:e},{0.0:e},{ph['crt'] / 1e3:e},\n")
+        ref = row.get("reference")
+        if ref and "error" not in ref:
+            rp = ref["phases_ms"]
+            csv.write(pre + f"REF-{row['function']}[{tag}],{ref['relerr_max']:e},{ref['relerr_med']:e},{ref['TFLOPS']:e},{ref['total_time_ms'] / 1e3:e},"
+                            f"{rp[0] / 1e3:e},{rp[1] / 1e3:e},{rp[2] / 1e3:e},{rp[3] / 1e3:e},\n")
+        nat = row.get("native")
+        if nat:
+            name = {"d": "DGEMM", "s": "SGEMM", "z": "ZGEMM", "c": "CGEMM"}[row["types"][-1]]
+            csv.write(pre + f"{name}[{tag}],{nat['relerr_max']:e},{nat['relerr_med']:e},{nat['TFLOPS']:e},,,,,,\n")
+        csv.flush()
+
     with open(a.out, "w") as f:
         for c in cfgs:
             try:
                 row = one(*c, reps=reps, with_ref=not a.no_ref)
             except Exception as e:
                 row = {"config": list(map(str, c)), "error": str(e)[:300]}
+            csv_rows(row)
             line = json.dumps(row)
             print(line, flush=True)
             f.write(line + "\n")
