@@ -127,6 +127,20 @@ int gemmul8_b200_gemm_host(gemmul8_b200_args *args_with_host_matrices, void *dev
 enum { GEMMUL8_PART_SCALE_A = 1, GEMMUL8_PART_SCALE_B = 2, GEMMUL8_PART_PRODUCT = 4 };
 int gemmul8_b200_gemm_part(gemmul8_b200_args *args, int parts, size_t row0, size_t row1, size_t col0, size_t col1);
 
+/* Low-memory call (real types, fast and accurate mode).  gemm() keeps the residue slices of ALL of op(A) and
+ * op(B) resident -- N (m + n) k bytes, 184 GiB at 65536^3 (GEMMul8/src/gemmul8.cu:27-60); the reference's
+ * README.md:3 points at a `memory-lt` branch for this, which is not in the tree.  Here C is produced in blocks of
+ * block_rows x block_cols (multiples of 256, or the whole dimension) and `args->work` only needs
+ * gemmul8_b200_worksize_blocked() bytes: N k (block_rows + block_cols) + N block_rows block_cols + 6 (m + n)
+ * (+ padding).  Result bits are those of gemmul8_b200_gemm (shifts are per row / column, residues and CRT per
+ * element, the accurate-mode bound is a maximum over blocks).  gemmul8_b200_plan_blocks picks the block sizes with
+ * the least re-encoding for a workspace of at most `max_bytes`.  timers_ns (GEMMUL8_FLAG_TIMERS) are the sums of the
+ * phases over all blocks, as in gemmul8_b200_gemm. */
+size_t gemmul8_b200_worksize_blocked(size_t m, size_t n, size_t k, unsigned num_moduli, size_t block_rows, size_t block_cols);
+int gemmul8_b200_plan_blocks(size_t m, size_t n, size_t k, unsigned num_moduli, size_t max_bytes,
+                             size_t *block_rows, size_t *block_cols, size_t *work_bytes);
+int gemmul8_b200_gemm_blocked(gemmul8_b200_args *args, size_t block_rows, size_t block_cols);
+
 /* Debug/parity: raw int32 product of modulus slice `j` (what the reference's cublasGemmEx at
  * gemmul8.cu:265 writes into C32i), column-major with leading dimension m_pad.  Requires the
  * slices to be present in `work` (GEMMUL8_FLAG_STAGE_SCALING or a full gemm call). */

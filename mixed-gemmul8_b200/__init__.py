@@ -26,7 +26,8 @@ FLAG_ONLY_SCALE_A, FLAG_SKIP_SCALE_A = 1 << 11, 1 << 12
 
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",
-    "gemmul8_b200_gemm_host", "gemmul8_b200_gemm_part", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
+    "gemmul8_b200_gemm_host", "gemmul8_b200_gemm_part",
+    "gemmul8_b200_worksize_blocked", "gemmul8_b200_plan_blocks", "gemmul8_b200_gemm_blocked", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
     "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
 )
 
@@ -84,6 +85,12 @@ def lib():
         L.gemmul8_b200_gemm_host.argtypes = [C.POINTER(Args), C.c_void_p]
         L.gemmul8_b200_gemm_part.restype = C.c_int
         L.gemmul8_b200_gemm_part.argtypes = [C.POINTER(Args), C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.gemmul8_b200_worksize_blocked.restype = C.c_size_t
+        L.gemmul8_b200_worksize_blocked.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, C.c_size_t, C.c_size_t]
+        L.gemmul8_b200_plan_blocks.restype = C.c_int
+        L.gemmul8_b200_plan_blocks.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, C.c_size_t] + [C.POINTER(C.c_size_t)] * 3
+        L.gemmul8_b200_gemm_blocked.restype = C.c_int
+        L.gemmul8_b200_gemm_blocked.argtypes = [C.POINTER(Args), C.c_size_t, C.c_size_t]
         L.gemmul8_b200_product_i32.restype = C.c_int
         L.gemmul8_b200_product_i32.argtypes = [C.POINTER(Args), C.c_uint, C.c_void_p, C.c_int]
         L.gemmul8_b200_modulus.restype = C.c_int
@@ -190,6 +197,30 @@ def gemm_part(args, parts, row0, row1, col0, col1):
     """One or more steps (PART_*) of the real fast-mode path on rows [row0, row1) x columns [col0, col1) of the full
     problem described by `args` (from make_args); see gemmul8_b200_gemm_part in include/gemmul8_b200.h."""
     _check(lib().gemmul8_b200_gemm_part(C.byref(args), parts, row0, row1, col0, col1))
+
+
+def workSizeBlocked(m, n, k, num_moduli, block_rows, block_cols):
+    """Bytes of `work` for gemm_blocked with these block sizes (0 if they are not multiples of 256 / whole dimensions)."""
+    return lib().gemmul8_b200_worksize_blocked(m, n, k, num_moduli, block_rows, block_cols)
+
+
+def plan_blocks(m, n, k, num_moduli, max_bytes):
+    """(block_rows, block_cols, work_bytes): the blocks with the least re-encoding whose workspace fits max_bytes."""
+    mb, nb, wb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _check(lib().gemmul8_b200_plan_blocks(m, n, k, num_moduli, max_bytes, C.byref(mb), C.byref(nb), C.byref(wb)))
+    return mb.value, nb.value, wb.value
+
+
+def gemm_blocked(handle, op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, work,
+                 block_rows, block_cols, flags=0):
+    """gemm() with a small workspace: C in blocks of block_rows x block_cols, `work` of workSizeBlocked() bytes
+    (gemmul8_b200_gemm_blocked; real types).  Same result bits as gemm()."""
+    stream = None
+    if handle is not None:
+        stream = handle.cuda_stream if hasattr(handle, "cuda_stream") else int(handle)
+    a = make_args(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, work, REAL_DEFAULT, stream, flags)
+    _check(lib().gemmul8_b200_gemm_blocked(C.byref(a), block_rows, block_cols))
+    return list(a.timers_ns)
 
 
 def gemm_host(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, dev_scratch,

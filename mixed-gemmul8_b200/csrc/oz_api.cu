@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 namespace oz {
 static std::atomic<unsigned long long> g_launches{0};
@@ -521,6 +523,226 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
     return GEMMUL8_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Low-memory call (the reference's README.md:3 points at a `memory-lt` branch that is not
+// in the tree).  gemm() keeps the residue slices of ALL of op(A) and op(B): N (m + n) k bytes, 184 GiB at
+// 65536^3.  Here C is produced in blocks of block_rows x block_cols and only the slices of one row block
+// and one column block (plus the residues of one C block) are resident:
+//     work = N k (block_rows + block_cols) + N block_rows block_cols + 6 (m + n) bytes (+ padding).
+// Shifts are per row of op(A) / column of op(B), residues and CRT per element, and the accurate-mode bound
+// only needs row / column maxima (atomicMax over blocks), so the result bits are those of gemm().  The
+// operand of the inner loop is re-encoded once per outer block unless all of it fits in one block.
+// ---------------------------------------------------------------------------------------------
+struct BlockPlan {
+    size_t mb, nb;          // block_rows, block_cols (multiples of 256, or the whole dimension)
+    bool outer_rows;        // true: for row blocks { for column blocks }, else the other way round
+    size_t lda8i, mb_pad, sizeA, sizeB, sizeC;
+    size_t off_A8i, off_B8i, off_C8u, off_sftA, off_sftB, off_rowmax, off_colmax, total;
+};
+
+bool carve_blocks(size_t m, size_t n, size_t k, unsigned N, size_t mb, size_t nb, BlockPlan &P) {
+    if (mb == 0 || nb == 0) return false;
+    P.mb = mb < m ? mb : m; P.nb = nb < n ? nb : n;
+    if ((P.mb < m && P.mb % 256) || (P.nb < n && P.nb % 256)) return false;
+    P.lda8i = ceil_to(k, 16);
+    P.mb_pad = ceil_to(P.mb, 4);
+    P.sizeA = P.lda8i * P.mb_pad;
+    P.sizeB = P.lda8i * P.nb;
+    P.sizeC = ceil_to(P.mb_pad * P.nb, 16);
+    size_t off = 0;
+    P.off_A8i = off;    off += P.sizeA * N;
+    P.off_B8i = off;    off += P.sizeB * N;
+    P.off_C8u = off;    off += P.sizeC * N;
+    P.off_sftA = off;   off += 2 * ceil_to(m, 16);
+    P.off_sftB = off;   off += 2 * ceil_to(n, 16);
+    P.off_rowmax = off; off += 4 * ceil_to(m, 16);
+    P.off_colmax = off; off += 4 * ceil_to(n, 16);
+    P.total = off;
+    const size_t Rb = (m + P.mb - 1) / P.mb, Cb = (n + P.nb - 1) / P.nb;
+    // elements encoded more than once: inner operand, once per outer block (unless it is a single block)
+    const size_t cost_rows_outer = Cb > 1 ? (Rb - 1) * n : 0, cost_cols_outer = Rb > 1 ? (Cb - 1) * m : 0;
+    P.outer_rows = cost_rows_outer <= cost_cols_outer;
+    return true;
+}
+
+// largest blocks that fit `max_bytes`: least re-encoding first, then the squarest block
+bool plan_blocks(size_t m, size_t n, size_t k, unsigned N, size_t max_bytes, BlockPlan &best) {
+    bool found = false;
+    double best_cost = 0;
+    const size_t tm = (m + 255) / 256, tn = (n + 255) / 256;
+    for (size_t Rb = 1; Rb <= tm; ++Rb) {
+        const size_t mb = Rb == 1 ? m : ((tm + Rb - 1) / Rb) * 256;
+        if (Rb > 1 && (m + mb - 1) / mb != Rb) continue;   // same block size as a smaller Rb
+        // widest nb for this mb: total is monotone in nb
+        size_t lo = 1, hi = tn, fit = 0;
+        while (lo <= hi) {
+            const size_t mid = (lo + hi) / 2;
+            BlockPlan P;
+            const size_t nb = mid == tn ? n : mid * 256;
+            if (carve_blocks(m, n, k, N, mb, nb, P) && P.total <= max_bytes) { fit = mid; lo = mid + 1; }
+            else hi = mid - 1;
+        }
+        if (!fit) continue;
+        // equalise the column blocks: same count, smallest width
+        const size_t Cb = (tn + fit - 1) / fit;
+        const size_t nbt = (tn + Cb - 1) / Cb;
+        BlockPlan P;
+        carve_blocks(m, n, k, N, mb, nbt == tn ? n : nbt * 256, P);
+        const double re = P.outer_rows ? (Cb > 1 ? (double)(Rb - 1) * n : 0.0) : (Rb > 1 ? (double)(Cb - 1) * m : 0.0);
+        // re-encoded elements (x k), plus a small charge per block for the tails of the persistent GEMM
+        const double cost = re * (double)k + 1e-3 * (double)(Rb * Cb) * (double)k * (double)(m + n);
+        if (!found || cost < best_cost) { best = P; best_cost = cost; found = true; }
+    }
+    return found;
+}
+
+int gemm_blocked_real(gemmul8_b200_args *a, const BlockPlan &P) {
+    const size_t m = a->m, n = a->n, k = a->k;
+    const unsigned N = a->num_moduli, ti = N - 2;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    uint8_t *work = static_cast<uint8_t *>(a->work);
+    int8_t *A8i     = reinterpret_cast<int8_t *>(work + P.off_A8i);
+    int8_t *B8i     = reinterpret_cast<int8_t *>(work + P.off_B8i);
+    uint8_t *C8u    = work + P.off_C8u;
+    int16_t *sftA   = reinterpret_cast<int16_t *>(work + P.off_sftA);
+    int16_t *sftB   = reinterpret_cast<int16_t *>(work + P.off_sftB);
+    int32_t *rowmax = reinterpret_cast<int32_t *>(work + P.off_rowmax);
+    int32_t *colmax = reinterpret_cast<int32_t *>(work + P.off_colmax);
+    const bool a_strided = a->op_A == GEMMUL8_OP_N, b_strided = a->op_B != GEMMUL8_OP_N;
+    const int ref_width  = oz::ref_reduce_width(a->dtype_A, a->dtype_B, a->dtype_C);
+    const size_t esA = elem_size(a->dtype_A), esB = elem_size(a->dtype_B), esC = elem_size(a->dtype_C);
+    const bool fast = a->fastmode != 0;
+    const float l2  = fast ? oz::host_tab::OZ_LOG2M_FAST[ti] : 0.f;
+    const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;
+    const size_t Rb = (m + P.mb - 1) / P.mb, Cb = (n + P.nb - 1) / P.nb;
+    auto rows_of = [&](size_t i, size_t &r0, size_t &r1) { r0 = i * P.mb; r1 = r0 + P.mb < m ? r0 + P.mb : m; };
+    auto cols_of = [&](size_t j, size_t &c0, size_t &c1) { c0 = j * P.nb; c1 = c0 + P.nb < n ? c0 + P.nb : n; };
+    auto Aptr = [&](size_t r0) { return static_cast<const uint8_t *>(a->A) + (a_strided ? r0 : r0 * a->lda) * esA; };
+    auto Bptr = [&](size_t c0) { return static_cast<const uint8_t *>(a->B) + (b_strided ? c0 : c0 * a->ldb) * esB; };
+
+    // phase times over all blocks (GEMMUL8_FLAG_TIMERS): an event at every phase boundary, summed per phase at the end
+    struct Marks {
+        bool on; cudaStream_t st; std::vector<std::pair<cudaEvent_t, int>> ev;   // (event, phase that ENDS here; -1 = start)
+        void mark(int phase) {
+            if (!on) return;
+            cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.emplace_back(e, phase);
+        }
+        void finish(double *out_ns) {
+            if (!on || ev.empty()) return;
+            cudaEventSynchronize(ev.back().first);
+            for (size_t i = 1; i < ev.size(); ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i - 1].first, ev[i].first);
+                if (ev[i].second >= 0) out_ns[ev[i].second] += (double)ms * 1e6;
+            }
+            for (auto &e : ev) cudaEventDestroy(e.first);
+        }
+    } timer{(a->flags & GEMMUL8_FLAG_TIMERS) != 0, st, {}};
+    timer.mark(-1);
+    if (!fast && k > 0) {
+        // accurate mode: row / column maxima of the bound product over all blocks, then all the shifts
+        // (reference: int8tc::scaling, GEMMul8/src/scaling.hpp:3053-3136)
+        OZ_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(int32_t) * m, st), "memset row maxima");
+        OZ_CUDA(cudaMemsetAsync(colmax, 0, sizeof(int32_t) * n, st), "memset col maxima");
+        oz::GemmProblem bp{};
+        bp.ld8i = P.lda8i; bp.sizeA = P.sizeA; bp.sizeB = P.sizeB; bp.num_slices = 1; bp.first_modulus = 0;
+        for (size_t o = 0; o < (P.outer_rows ? Rb : Cb); ++o) {
+            for (size_t q = 0; q < (P.outer_rows ? Cb : Rb); ++q) {
+                const size_t i = P.outer_rows ? o : q, j = P.outer_rows ? q : o;
+                size_t r0, r1, c0, c1;
+                rows_of(i, r0, r1); cols_of(j, c0, c1);
+                const bool newA = P.outer_rows ? q == 0 : (Rb > 1 || o == 0);
+                const bool newB = P.outer_rows ? (Cb > 1 || o == 0) : q == 0;
+                if (newA) OZ_CUDA(oz::launch_bound_extract(a->dtype_A, a_strided, Aptr(r0), a->lda, r1 - r0, k, A8i, P.lda8i, sftA + r0, st), "bound extract A");
+                if (newB) OZ_CUDA(oz::launch_bound_extract(a->dtype_B, b_strided, Bptr(c0), a->ldb, c1 - c0, k, B8i, P.lda8i, sftB + c0, st), "bound extract B");
+                bp.A8i = A8i; bp.B8i = B8i; bp.rowsA = r1 - r0; bp.rowsB = c1 - c0; bp.rowmax = rowmax + r0; bp.colmax = colmax + c0;
+                OZ_CUDA(oz::launch_gemm_tcgen05(bp, oz::EPI_ABSMAX, st), "bound product");
+            }
+        }
+        const float l2a = oz::host_tab::OZ_LOG2M_ACC[ti];
+        OZ_CUDA(oz::launch_accurate_shifts(m, rowmax, l2a, sftA, st), "accurate shifts A");
+        OZ_CUDA(oz::launch_accurate_shifts(n, colmax, l2a, sftB, st), "accurate shifts B");
+        timer.mark(0);
+    }
+
+    oz::GemmProblem gp{};
+    gp.ld8i = P.lda8i; gp.sizeA = P.sizeA; gp.sizeB = P.sizeB; gp.num_slices = N; gp.first_modulus = 0;
+    gp.ldc8u = P.mb_pad; gp.sizeC = P.sizeC; gp.A8i = A8i; gp.B8i = B8i; gp.C8u = C8u;
+    for (size_t o = 0; o < (P.outer_rows ? Rb : Cb); ++o) {
+        for (size_t q = 0; q < (P.outer_rows ? Cb : Rb); ++q) {
+            const size_t i = P.outer_rows ? o : q, j = P.outer_rows ? q : o;
+            size_t r0, r1, c0, c1;
+            rows_of(i, r0, r1); cols_of(j, c0, c1);
+            const bool newA = P.outer_rows ? q == 0 : (Rb > 1 || o == 0);
+            const bool newB = P.outer_rows ? (Cb > 1 || o == 0) : q == 0;
+            // fast-mode shifts of a re-encoded block are already known after its first visit
+            const bool firstA = P.outer_rows ? true : o == 0, firstB = P.outer_rows ? o == 0 : true;
+            if (newA && k > 0) {
+                int rc = scale_operand(a->dtype_A, a_strided, Aptr(r0), a->lda, r1 - r0, k, ref_width, l2, N, A8i, P.lda8i, P.sizeA, sftA + r0,
+                                       fast && firstA, st);
+                if (rc) return rc;
+            }
+            if (newB && k > 0) {
+                int rc = scale_operand(a->dtype_B, b_strided, Bptr(c0), a->ldb, c1 - c0, k, ref_width, l2, N, B8i, P.lda8i, P.sizeB, sftB + c0,
+                                       fast && firstB, st);
+                if (rc) return rc;
+            }
+            timer.mark(0);
+            gp.rowsA = r1 - r0; gp.rowsB = c1 - c0;
+            OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+            timer.mark(1);
+            OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, r1 - r0, c1 - c0, C8u, P.mb_pad, P.sizeC,
+                                   static_cast<uint8_t *>(a->C) + (c0 * a->ldc + r0) * esC, a->ldc, sftA + r0, sftB + c0, a->alpha, a->beta, st),
+                    "crt");
+            timer.mark(3);
+        }
+    }
+    timer.finish(a->timers_ns);
+    return GEMMUL8_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gemmul8_b200_worksize_blocked(size_t m, size_t n, size_t k, unsigned num_moduli, size_t block_rows, size_t block_cols) {
+    BlockPlan P;
+    if (num_moduli < 2 || num_moduli > 20 || !carve_blocks(m, n, k, num_moduli, block_rows, block_cols, P)) return 0;
+    return P.total;
+}
+
+int gemmul8_b200_plan_blocks(size_t m, size_t n, size_t k, unsigned num_moduli, size_t max_bytes, size_t *block_rows, size_t *block_cols,
+                             size_t *work_bytes) {
+    BlockPlan P;
+    if (num_moduli < 2 || num_moduli > 20) return fail(GEMMUL8_ERR_ARGUMENT, "num_moduli must be in 2..20");
+    if (!m || !n) { if (block_rows) *block_rows = m; if (block_cols) *block_cols = n; if (work_bytes) *work_bytes = 0; return GEMMUL8_OK; }
+    if (!plan_blocks(m, n, k, num_moduli, max_bytes, P)) return fail(GEMMUL8_ERR_ARGUMENT, "plan_blocks: max_bytes is below the 256 x 256 block minimum");
+    if (block_rows) *block_rows = P.mb;
+    if (block_cols) *block_cols = P.nb;
+    if (work_bytes) *work_bytes = P.total;
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t block_cols) {
+    if (a) for (double &t : a->timers_ns) t = 0.0;
+    int rc = check_args(a);
+    if (rc) return rc;
+    if (is_complex(a->dtype_C)) return fail(GEMMUL8_ERR_ARGUMENT, "gemm_blocked: real types only (complex sizes that need it exceed k <= 2^16 first)");
+    if (a->m == 0 || a->n == 0) return GEMMUL8_OK;
+    BlockPlan P;
+    if (!carve_blocks(a->m, a->n, a->k, a->num_moduli, block_rows, block_cols, P))
+        return fail(GEMMUL8_ERR_ARGUMENT, "gemm_blocked: block sizes must be multiples of 256 (or cover the whole dimension)");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+        return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    return gemm_blocked_real(a, P);
+}
+
+}  // extern "C"
 
 // Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C.  The H2D
 // stream brings A row blocks and B column blocks alternately (A0, B0, A1, B1, ...); as soon as block
@@ -655,6 +877,8 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     OZ_CUDA(cudaStreamSynchronize(st), "sync");
     return GEMMUL8_OK;
 }
+
+extern "C" {
 
 int gemmul8_b200_gemm_host(gemmul8_b200_args *h, void *dev_scratch) {
     int rc = check_args(h);

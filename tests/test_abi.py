@@ -69,6 +69,37 @@ def test_layout_is_the_reference_carve(g):
     assert Lk.total == g.workSize(m, n, k, N, g.COMPLEX_KARATSUBA_MULT)
 
 
+def test_blocked_worksize_and_plan(g):
+    """Low-memory call: workspace formula, block constraints and the planner (host logic only)."""
+    m = n = k = 65536
+    N = 14
+    full = g.workSizeBlocked(m, n, k, N, m, n)
+    assert full < g.workSize(m, n, k, N)                          # no int32 product matrix in our carve
+    ws = g.workSizeBlocked(m, n, k, N, 16384, 16384)
+    assert ws == N * k * 32768 + N * 16384 * 16384 + 6 * (m + n)
+    assert g.workSizeBlocked(m, n, k, N, 1000, 16384) == 0        # block sizes: multiples of 256 ...
+    assert g.workSizeBlocked(1000, 900, 64, N, 1000, 900) > 0     # ... or the whole dimension
+    assert g.workSizeBlocked(1000, 900, 64, N, 4096, 4096) == g.workSizeBlocked(1000, 900, 64, N, 1000, 900)
+    for budget in (64 << 30, 40 << 30, 8 << 30, 1 << 30):
+        mb, nb, wb = g.plan_blocks(m, n, k, N, budget)
+        assert wb <= budget and wb == g.workSizeBlocked(m, n, k, N, mb, nb)
+        assert mb % 256 == 0 and nb % 256 == 0 and mb >= 256 and nb >= 256
+    mb, nb, wb = g.plan_blocks(m, n, k, N, 64 << 30)
+    assert mb == m and -(-n // nb) <= 16                           # 64 GiB: all of A resident (no re-encoding), a handful of column blocks
+    assert g.plan_blocks(3000, 2000, 500, 9, 1 << 40)[:2] == (3000, 2000)     # everything fits: one block
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        mm, nn, kk = (int(x) for x in rng.integers(1, 20000, 3))
+        NN = int(rng.integers(2, 21))
+        lo = g.workSizeBlocked(mm, nn, kk, NN, 256, 256)
+        budget = int(rng.integers(lo, 4 * lo + 1000))
+        mb, nb, wb = g.plan_blocks(mm, nn, kk, NN, budget)
+        assert lo <= wb <= budget and wb == g.workSizeBlocked(mm, nn, kk, NN, mb, nb)
+        assert (mb == mm or mb % 256 == 0) and (nb == nn or nb % 256 == 0)
+    with pytest.raises(g.Gemmul8Error):
+        g.plan_blocks(m, n, k, N, 1 << 20)                         # below the 256 x 256 minimum
+
+
 def test_moduli_and_weights_exposed(g):
     mods = [g.modulus(j) for j in range(20)]
     assert mods == [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181, 179, 173]

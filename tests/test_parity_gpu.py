@@ -282,6 +282,55 @@ def test_block_wise_entry_equals_single_call(g):
         g.gemm_part(args, g.PART_PRODUCT, 100, 200, 0, n)       # row0 not a multiple of 256
 
 
+BLOCKED_CASES = [
+    # m, n, k, N, fast, opA, opB, dtA, dtB, dtC, block_rows, block_cols, alpha, beta
+    (1300, 900, 700, 14, 1, 0, 0, "float64", "float64", "float64", 512, 256, 1.0, 0.0),
+    (1300, 900, 700, 14, 0, 0, 0, "float64", "float64", "float64", 512, 256, 1.0, 0.0),
+    (1300, 900, 700, 15, 1, 1, 1, "float64", "float64", "float64", 256, 512, 0.75, -1.5),
+    (1300, 900, 700, 9, 0, 1, 0, "float64", "float64", "float64", 1300, 256, 1.0, 0.0),      # one row block: A encoded once
+    (900, 1300, 333, 6, 1, 0, 1, "float32", "float32", "float32", 256, 1300, 1.0, 0.0),      # one column block
+    (900, 1300, 333, 7, 0, 0, 0, "float32", "float32", "float32", 768, 768, 1.0, 0.0),
+    (1025, 513, 2048, 12, 1, 0, 0, "float64", "float32", "float64", 256, 256, 1.0, 0.0),     # ragged last blocks of 1 row / 1 column
+    (1025, 513, 2048, 17, 0, 0, 0, "float32", "float64", "float64", 512, 512, 1.0, 1.0),
+    (700, 600, 500, 14, 1, 0, 0, "float64", "float64", "float64", 700, 600, 1.0, 0.0),       # everything in one block
+]
+
+
+@pytest.mark.parametrize("m,n,k,N,fast,opA,opB,dtA,dtB,dtC,mb,nb,alpha,beta", BLOCKED_CASES)
+def test_low_memory_blocked_call_equals_single_call(g, m, n, k, N, fast, opA, opB, dtA, dtB, dtC, mb, nb, alpha, beta):
+    """gemmul8_b200_gemm_blocked (C block by block, slices of one row block and one column block resident) gives the
+    bits of gemmul8_b200_gemm, in fast and accurate mode, with a workspace several times smaller."""
+    torch = torch_()
+    A, B = operands(g, m, n, k, opA, opB, getattr(torch, dtA), getattr(torch, dtB), seedB=77)
+    C0 = g.phi_matrix(m, n, 1.0, getattr(torch, dtC), seed=5)
+    want, _ = run_ours(g, m, n, k, N, fast, A, B, opA, opB, alpha=alpha, beta=beta, C0=C0)
+    ws = g.workSizeBlocked(m, n, k, N, mb, nb)
+    assert 0 < ws and (ws < g.workSize(m, n, k, N))
+    guard = 4096
+    work = torch.full((ws + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    C = C0.clone()
+    g.gemm_blocked(None, opA, opB, m, n, k, alpha, A, A.shape[1], B, B.shape[1], beta, C, m, N, fast, work, mb, nb)
+    torch.cuda.synchronize()
+    assert torch.equal(C, want)
+    assert bool((work[ws:] == 0xA5).all())                       # nothing written beyond workSizeBlocked()
+
+
+def test_low_memory_planned_blocks(g):
+    """Blocks chosen by gemmul8_b200_plan_blocks for a budget of a quarter of workSize(): same bits."""
+    torch = torch_()
+    m, n, k, N = 2500, 3100, 1024, 14
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=8)
+    want, _ = run_ours(g, m, n, k, N, True, A, B)
+    mb, nb, ws = g.plan_blocks(m, n, k, N, g.workSize(m, n, k, N) // 4)
+    assert (mb < m or nb < n) and ws <= g.workSize(m, n, k, N) // 4
+    work = torch.zeros(ws, dtype=torch.uint8, device="cuda")
+    C = torch.zeros_like(want)
+    t = g.gemm_blocked(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, mb, nb, flags=g.FLAG_TIMERS)
+    assert torch.equal(C, want) and t[1] > 0
+    with pytest.raises(g.Gemmul8Error):
+        g.gemm_blocked(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, 300, nb)     # not a multiple of 256
+
+
 def test_cuda_graph_capture_and_replay(g):
     """The call is stream-ordered with no host synchronisation, allocation or constant upload (the reference does
     2 + 4N device syncs and 2 cudaMemcpyToSymbol per call, gemmul8.cu:10-18, :236-241): it can be captured into a
