@@ -157,6 +157,42 @@ def test_known_answer_1024(g, fast, want):
     assert abs(err - want) <= 5e-7 * want, err       # the CSV prints 7 significant digits
 
 
+def _published_rows():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "published_d_accuracy_GH200.csv")
+    rows = [line.strip().split(",") for line in open(path)]
+    moduli = [int(x) for x in rows[0][2:] if x]
+    out = {}
+    for f in rows[1:]:
+        k = int(f[1].split("k=")[1].rstrip(")"))
+        out[(float(f[0]), k, f[1].startswith("OS2-fast"))] = dict(zip(moduli, (float(x) for x in f[2:] if x)))
+    return out
+
+
+@pytest.mark.parametrize("phi", [0.5, 1.0, 2.0, 3.0, 4.0])
+@pytest.mark.parametrize("k", [1024, 2048])
+def test_published_accuracy_table(g, phi, k):
+    """The reference's published accuracy table (test_double accuracy_check, m = n = 1024, 2..20 moduli, fast and
+    accurate mode: GEMMul8/testing/results_in_paper/oz2_results_d_accuracy_NVIDIA_GH200_480GB_2025-04-09_02-40-54.csv,
+    fixture tests/golden/published_d_accuracy_GH200.csv) reproduced cell by cell: 38 known answers per (phi, k).
+    (profiles/r01_reference_drivers.md: the reference's unmodified driver linked against this library prints all 760
+    cells of the table identically.)"""
+    torch = torch_()
+    m = n = 1024
+    pub = _published_rows()
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, phi=phi)
+    C1, C2 = g.dd_gemm(m, n, k, A, m, B, k)
+    bad = []
+    for fast in (True, False):
+        want = pub[(phi, k, fast)]
+        for N in range(2, 21):
+            C, _ = run_ours(g, m, n, k, N, fast, A, B)
+            err = (((C - C1) - C2) / C1).abs().max().item()
+            if abs(err - want[N]) > 2e-6 * want[N]:      # 7 printed digits; our error formula is plain double, theirs double-double
+                bad.append((fast, N, err, want[N]))
+    assert not bad, bad
+
+
 def test_tcgen05_gemm_equals_cuda_core_gemm(g):
     """int32 products and residues of the tensor-core kernel vs the dp4a cross-check kernel (ragged tiles)."""
     torch = torch_()
