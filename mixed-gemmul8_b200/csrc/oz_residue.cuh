@@ -51,17 +51,22 @@ __device__ __forceinline__ int residue_reference(float a, const ModConst &c) {
 }
 // The routes used instead: one fp instruction per (element, modulus) and no conversion-pipe work
 // (FRND / F2F / F2I issue at a quarter of the FP64 rate on sm_100 and bound the sequence above).
-//   * ANY quotient q with |a - q*m| <= 1.5 m followed by "fold once towards zero from either side"
-//     lands on the symmetric residue (ties only exist for m = 256, where +-128 are the same int8);
-//   * q = rint(a * rcp) comes out of the low word of fma(a, rcp, 1.5*2^52) (needs |a * rcp| < 2^51;
-//     |a/m - q| <= 0.5 + 2^-53 |a/m| < 0.6), and t = a - q*m is evaluated modulo 2^32 on the low
-//     words (|t| < 2^9, so nothing is lost).  Valid for |a| < 2^57 (fp64) / 2^24 (fp32);
+//   * q = floor(a * rcp) comes out of the low word of fma_rd(a, rcp, 1.5*2^52) (needs |a * rcp| < 2^51).  rcp is
+//     1/m rounded, so the product is off by e, |e| <= 2^-53 |a/m| < 0.1 for |a| < 2^57 (fp32: 2^-24 |a/m| < 0.01
+//     for |a| < 2^24), and q is floor(a/m) or a neighbour:
+//         q = floor(a/m)     : t = a - q m = r in [0, m)
+//         q = floor(a/m) - 1 : only if r/m + e < 0,  i.e. r < 0.1 m : t = r + m
+//         q = floor(a/m) + 1 : only if r/m + e >= 1, i.e. r > 0.9 m : t = r - m, already the symmetric residue
+//     so ONE fold, "t > m/2 ? t - m : t", lands on the symmetric residue in every case (m = 256: r = 128 stays
+//     +128, the same int8 as the reference's -128).  t is evaluated modulo 2^32 on the low words (|t| < 2^10).
+//     Valid for |a| < 2^57 (fp64) / 2^24 (fp32);
+//   * m = 256 (modulus 0) needs no arithmetic at all: the int8 is the low byte of a;
 //   * larger values (more than 15 moduli) are split exactly as a = h * 2^32 + l, |h| < 2^57,
 //     |l| < 2^32, and joined as (res(h) * (2^32 mod m) + res(l)) mod m.
 template <typename R> struct SmallLimit;
 template <> struct SmallLimit<double> { static constexpr double value = 0x1p57; };
 template <> struct SmallLimit<float> { static constexpr float value = 0x1p24f; };
-__device__ __forceinline__ int fold_once(int ti, int half, int m) {
+__device__ __forceinline__ int fold_once(int ti, int half, int m) {   // [-m/2 - m, m/2 + m] -> symmetric
     asm("{\n\t.reg .pred p, q;\n\t"
         "setp.gt.s32 p, %0, %1;\n\t"
         "@p sub.s32 %0, %0, %2;\n\t"
@@ -71,16 +76,24 @@ __device__ __forceinline__ int fold_once(int ti, int half, int m) {
         : "r"(half), "r"(m), "r"(-half));
     return ti;
 }
+__device__ __forceinline__ int fold_down(int ti, int half, int m) {   // (-m/2, m + m/2) -> symmetric
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.s32 p, %0, %1;\n\t"
+        "@p sub.s32 %0, %0, %2;\n\t}"
+        : "+r"(ti)
+        : "r"(half), "r"(m));
+    return ti;
+}
 // low 32 bits of the (exactly integer) value a, two's complement
 __device__ __forceinline__ int low_word(double a) { return (int)__double2ll_rz(a); }
 __device__ __forceinline__ int low_word(float a) { return __float2int_rz(a); }
 __device__ __forceinline__ int residue_small(double a, int a_lo, const ModConst &c) {
-    const int q = __double2loint(fma(a, c.rcp, 6755399441055744.0));  // 1.5 * 2^52
-    return fold_once(q * c.neg_mi + a_lo, c.half, c.m);
+    const int q = __double2loint(__fma_rd(a, c.rcp, 6755399441055744.0));  // 1.5 * 2^52
+    return fold_down(q * c.neg_mi + a_lo, c.half, c.m);
 }
 __device__ __forceinline__ int residue_small(float a, int a_lo, const ModConst &c) {
-    const int q = __float_as_int(__fmaf_rn(a, c.rcpf, 12582912.0f)) - 0x4B400000;  // 1.5 * 2^23
-    return fold_once(q * c.neg_mi + a_lo, c.half, c.m);
+    const int q = __float_as_int(__fmaf_rd(a, c.rcpf, 12582912.0f)) - 0x4B400000;  // 1.5 * 2^23
+    return fold_down(q * c.neg_mi + a_lo, c.half, c.m);
 }
 // exact residue of an int t, |t| < 2^22, by the same trick in fp32
 __device__ __forceinline__ int residue_int(int t, const ModConst &c) {
@@ -99,9 +112,10 @@ __device__ __forceinline__ int residue_big(double h, int h_lo, double l, int l_l
 // keeps the kernel at 64 registers); SPLIT = true (launched for 16+ moduli): they take the split route.
 template <int G, bool SPLIT, typename Store>
 __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned num_moduli, bool reference_chain, Store &&store) {
-    bool small = true;
+    unsigned top = 0;   // |v| < 2^57 on the high words (integer compare: keeps the test off the FP64 pipe)
 #pragma unroll
-    for (int e = 0; e < G; ++e) small &= fabs(v[e]) < 0x1p57;
+    for (int e = 0; e < G; ++e) top = max(top, (unsigned)__double2hiint(v[e]) & 0x7fffffffu);
+    const bool small = top < 0x43800000u;
     if (reference_chain || (!SPLIT && !small)) {
         for (unsigned j = 0; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
@@ -117,7 +131,8 @@ __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned n
             lo[e] = low_word(v[e]);
             asm volatile("" : "+r"(lo[e]));   // computed once: do not rematerialise the F2I inside the modulus loop
         }
-        for (unsigned j = 0; j < num_moduli; ++j) {
+        store(0u, lo);   // m_0 = 256: the low byte
+        for (unsigned j = 1; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
             int r[G];
 #pragma unroll
@@ -135,7 +150,8 @@ __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned n
             llo[e] = low_word(l[e]);
             asm volatile("" : "+r"(hlo[e]), "+r"(llo[e]));
         }
-        for (unsigned j = 0; j < num_moduli; ++j) {
+        store(0u, llo);  // 2^32 = 0 mod 256
+        for (unsigned j = 1; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
             const int p32    = dev_tab::OZ_POW32[j];
             int r[G];
@@ -151,9 +167,10 @@ __device__ __forceinline__ void residues_of(const double (&v)[G], unsigned num_m
 }
 template <int G, bool SPLIT, typename Store>
 __device__ __forceinline__ void residues_of(const float (&v)[G], unsigned num_moduli, bool reference_chain, Store &&store) {
-    bool small = true;
+    unsigned top = 0;   // |v| < 2^24
 #pragma unroll
-    for (int e = 0; e < G; ++e) small &= fabsf(v[e]) < 0x1p24f;
+    for (int e = 0; e < G; ++e) top = max(top, (unsigned)__float_as_int(v[e]) & 0x7fffffffu);
+    const bool small = top < 0x4B800000u;
     if (reference_chain) {
         for (unsigned j = 0; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
@@ -169,7 +186,8 @@ __device__ __forceinline__ void residues_of(const float (&v)[G], unsigned num_mo
             lo[e] = low_word(v[e]);
             asm volatile("" : "+r"(lo[e]));
         }
-        for (unsigned j = 0; j < num_moduli; ++j) {
+        store(0u, lo);
+        for (unsigned j = 1; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
             int r[G];
 #pragma unroll
@@ -208,6 +226,11 @@ template <typename R> struct Pow2 {
         R y = x * f1;
         if (two) y *= f2;
         if constexpr (sizeof(R) == 8) return trunc(y); else return truncf(y);
+    }
+    // the same when `two` is known to be false (callers branch once per warp: keeps the second multiply and its
+    // selects out of the common path)
+    __device__ __forceinline__ R one(R x) const {
+        if constexpr (sizeof(R) == 8) return trunc(x * f1); else return truncf(x * f1);
     }
 };
 

@@ -196,39 +196,63 @@ __global__ void __launch_bounds__(W) fast_shift_strided_kernel(const T *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// encode, contiguous vectors.  One thread = 4 consecutive k of one vector (the LSU sweet spot:
-// 2 x 16-byte loads in, one 4-byte store per modulus out, every warp store is a full 128-byte line).
-// grid = (ceil(ld8i/4 / 256), nvec)
+// encode, contiguous vectors.  One warp = 512 consecutive k of one vector: coalesced 16-byte loads (lane ==
+// 16-byte chunk), a transpose through the warp's private shared-memory slab (XOR swizzle: conflict-free both
+// ways, only __syncwarp), then each lane encodes 16 consecutive k and stores 16 bytes per modulus (a warp
+// writes 4 full 128-byte lines).  16 elements per thread amortise the per-modulus constants and the store
+// address over 16 residues (the 4-per-thread version spent a third of its issue slots there).
+// grid = (ceil(ld8i / 512), ceil(nvec / 8)), 256 threads
 // ---------------------------------------------------------------------------------------------
 template <typename R, bool SPLIT>
-__global__ void __launch_bounds__(256, 4) encode_contig_kernel(const R *__restrict__ X, size_t ld, size_t len,
+__global__ void __launch_bounds__(256, SPLIT ? 2 : 3) encode_contig_kernel(const R *__restrict__ X, size_t ld, size_t nvec, size_t len,
                                                             const int16_t *__restrict__ sft_neg, unsigned num_moduli,
-                                                            int8_t *__restrict__ out, size_t ld8i, size_t inc, bool ref_chain) {
-    const size_t vec = blockIdx.y;
-    const size_t g   = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 along k
-    const size_t i0  = g * 4;
-    if (i0 >= ld8i) return;
-    const Pow2<R> scale(-(int)sft_neg[vec]);
-    const R *__restrict__ p = X + vec * ld;
-    R v[4];
-    if (i0 + 3 < len && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
-        if constexpr (sizeof(R) == 8) {
-            const double2 a = *reinterpret_cast<const double2 *>(p + i0);
-            const double2 b = *reinterpret_cast<const double2 *>(p + i0 + 2);
-            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-        } else {
-            const float4 a = *reinterpret_cast<const float4 *>(p + i0);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        }
+                                                            int8_t *__restrict__ out, size_t ld8i, size_t inc, bool aligned, bool ref_chain) {
+    constexpr int EPC = 16 / sizeof(R);          // elements per 16-byte chunk
+    constexpr int CPT = 16 / EPC;                // chunks per thread (16 elements)
+    constexpr int CHUNKS = 32 * CPT;             // per warp tile of 512 elements
+    __shared__ uint4 slab_all[8][CHUNKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t vec = (size_t)blockIdx.y * 8 + warp;
+    if (vec >= nvec) return;
+    const size_t k0 = (size_t)blockIdx.x * 512;
+    uint4 *__restrict__ slab = slab_all[warp];
+    const R *__restrict__ p = X + vec * ld + k0;
+    auto slot = [](int c) { return c ^ ((c >> 3) & (CPT - 1)); };
+    if (aligned && k0 + 512 <= len) {
+        uint4 x[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) x[i] = __ldg(reinterpret_cast<const uint4 *>(p) + i * 32 + lane);
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) slab[slot(i * 32 + lane)] = x[i];
     } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (i0 + e < len) ? p[i0 + e] : R(0);
-    }
+        for (int i = 0; i < CPT; ++i) {
+            const int c = i * 32 + lane;
+            R e[EPC];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = scale(v[e]);
-    int8_t *__restrict__ o = out + vec * ld8i + i0;
-    residues_of<4, SPLIT>(v, num_moduli, ref_chain, [&](unsigned j, const int (&r)[4]) {
-        *reinterpret_cast<uint32_t *>(o + (size_t)j * inc) = pack4(r[0], r[1], r[2], r[3]);
+            for (int q = 0; q < EPC; ++q) e[q] = (k0 + (size_t)c * EPC + q < len) ? p[(size_t)c * EPC + q] : R(0);
+            slab[slot(c)] = *reinterpret_cast<const uint4 *>(e);
+        }
+    }
+    __syncwarp();
+    const size_t kb = k0 + 16 * lane;
+    if (kb >= ld8i) return;
+    R v[16];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) *reinterpret_cast<uint4 *>(&v[j * EPC]) = slab[slot(CPT * lane + j)];
+    const Pow2<R> scale(-(int)sft_neg[vec]);     // one vector per warp: the rare two-factor case is warp-uniform
+    if (scale.two) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = scale(v[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = scale.one(v[e]);
+    }
+    int8_t *__restrict__ o = out + vec * ld8i + kb;
+    residues_of<16, SPLIT>(v, num_moduli, ref_chain, [&](unsigned j, const int (&q)[16]) {
+        *reinterpret_cast<uint4 *>(o + (size_t)j * inc) =   // ld8i % 16 == 0 and kb % 16 == 0
+            make_uint4(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]), pack4(q[8], q[9], q[10], q[11]),
+                       pack4(q[12], q[13], q[14], q[15]));
     });
 }
 
@@ -247,7 +271,24 @@ __global__ void __launch_bounds__(256, SPLIT ? 2 : 4) encode_strided_kernel(cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t v0 = (size_t)blockIdx.y * 32;
     const size_t k0 = (size_t)blockIdx.x * 128;
-    {
+    if (v0 + 32 <= nvec && k0 + 128 <= len) {
+        // interior tile: no bounds checks, one 64-bit pointer stepped by 8 rows, all 16 loads in flight
+        const Pow2<R> scale(-(int)sft_neg[v0 + lane]);
+        const R *__restrict__ p = X + v0 + lane + (k0 + warp) * ld;
+        const size_t step = 8 * ld;
+        R x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { x[i] = *p; p += step; }
+        R *__restrict__ t = tile + warp * 32;
+        if (__any_sync(0xffffffffu, scale.two)) {   // shifts beyond +-1022: two exact factors
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i * 8 * 32 + ((lane + 4 * (i >> 1)) & 31)] = scale(x[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)    // kk = warp + 8 i, so kk >> 4 == i >> 1
+                t[i * 8 * 32 + ((lane + 4 * (i >> 1)) & 31)] = scale.one(x[i]);
+        }
+    } else {
         const size_t vec = v0 + lane;
         const bool active = vec < nvec;
         const Pow2<R> scale(active ? -(int)sft_neg[vec] : 0);
@@ -410,13 +451,15 @@ static cudaError_t run_encode(bool strided, const void *X, size_t ld, size_t nve
         kern<<<grid, 256, 0, st>>>(static_cast<const R *>(X), ld, nvec, len, sft_neg, num_moduli, out, ld8i, inc, ref_chain);
         count_launch();
     } else {
-        // blockIdx.y is limited to 65535: walk the vectors in slabs
-        for (size_t v0 = 0; v0 < nvec; v0 += 65535) {
-            const size_t nv = nvec - v0 < 65535 ? nvec - v0 : 65535;
-            dim3 grid((unsigned)((ld8i / 4 + 255) / 256), (unsigned)nv);
+        // blockIdx.y is limited to 65535: walk the vectors in slabs of 8 x 65535
+        const bool aligned = (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (ld * sizeof(R)) % 16 == 0;
+        constexpr size_t SLAB = 8 * (size_t)65535;
+        for (size_t v0 = 0; v0 < nvec; v0 += SLAB) {
+            const size_t nv = nvec - v0 < SLAB ? nvec - v0 : SLAB;
+            dim3 grid((unsigned)((ld8i + 511) / 512), (unsigned)((nv + 7) / 8));
             auto kern = num_moduli >= 16 ? encode_contig_kernel<R, true> : encode_contig_kernel<R, false>;
-            kern<<<grid, 256, 0, st>>>(static_cast<const R *>(X) + v0 * ld, ld, len, sft_neg + v0, num_moduli, out + v0 * ld8i,
-                                       ld8i, inc, ref_chain);
+            kern<<<grid, 256, 0, st>>>(static_cast<const R *>(X) + v0 * ld, ld, nv, len, sft_neg + v0, num_moduli, out + v0 * ld8i,
+                                       ld8i, inc, aligned, ref_chain);
             count_launch();
         }
     }
