@@ -301,6 +301,29 @@ def main():
         out["native_dgemm_tflops"] = flops / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e12
         del Cn
 
+    # ---- the north-star target: beat native DGEMM at an accuracy at least equal to native DGEMM's ----
+    # (14 moduli in fast mode are slightly less accurate than native DGEMM on this input; 15 are more accurate)
+    if rank == 0 and not multi and not big and N == 14 and fast and "native_dgemm_tflops" in out:
+        for N2 in (15, 16, 17):
+            work2 = torch.empty(g.workSize(m, n, k, N2), dtype=torch.uint8, device="cuda")
+            for _ in range(2):
+                g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, Cm, m, N2, True, work2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, Cm, m, N2, True, work2)
+            e1.record()
+            torch.cuda.synchronize()
+            acc2 = accuracy_sample(g, torch, m, n, k, A, B, Cm)
+            del work2
+            out["accuracy_matched"] = {"moduli": N2, "mode": "fast", "value": flops / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e12, "unit": "TFLOPS",
+                                       "relerr_max": acc2["relerr_max"], "relerr_med": acc2["relerr_med"],
+                                       "native_dgemm_relerr_max": acc2["native_dgemm_relerr_max"], "native_dgemm_tflops": out["native_dgemm_tflops"],
+                                       "note": "smallest num_moduli (fast mode) whose max relative error is at or below native cuBLAS DGEMM's on the same sample"}
+            if acc2["relerr_max"] <= acc2["native_dgemm_relerr_max"]:
+                break
+        step()      # restore C of the headline configuration for the checks below
+
     # ---- end-to-end through the host-buffer entry point ----
     if not args.no_e2e and not multi and not args.lowmem:
         hA = torch.empty((k, m), dtype=torch.float64, pin_memory=True).copy_(A)
