@@ -241,17 +241,27 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    live_phases = not multi and not args.lowmem
+    if live_phases:
+        g.phase_log_collect()       # empty the log
     for _ in range(args.steps):
-        step()                      # asynchronous calls, no instrumentation inside the timed region
+        step(g.FLAG_PHASE_LOG if live_phases else 0)   # asynchronous calls; the only instrumentation is 4 event records per call
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     launches = g.launch_count() - launches0
-    # per-phase split from a few instrumented calls outside the timed region (FLAG_TIMERS brackets the phases with events)
-    phase, psteps = [0.0] * 4, (1 if big else 3)
-    for _ in range(psteps):
-        phase = [a + b for a, b in zip(phase, step(g.FLAG_TIMERS))]
+    if live_phases:
+        # phase boundaries were recorded as events INSIDE the timed region (FLAG_PHASE_LOG: no host wait anywhere)
+        phase, psteps = g.phase_log_collect()
+        phase_how = "CUDA events recorded on the launching stream inside the timed region, no synchronisation between or after the calls"
+    else:
+        # per-phase split from a few instrumented calls outside the timed region (FLAG_TIMERS brackets the phases with events)
+        phase, psteps = [0.0] * 4, (1 if big else 3)
+        for _ in range(psteps):
+            phase = [a + b for a, b in zip(phase, step(g.FLAG_TIMERS))]
+        phase_how = ("instrumented calls after the timed region (a synchronisation follows each call, so the clock recovers a little: "
+                     "the sum of the phases is below ms_per_step)")
     barrier()
     if multi:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -273,8 +283,7 @@ def main():
     out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                        "traffic": ncu_traffic(m_loc if multi else m, n_loc if multi else n, k, N), "kernel": dominant_kernel() + " (all moduli in one launch, residue reduction in the epilogue)", "kernel_ms": gemm_ms,
                        "peak_source": f"2 x bf16 {'sustained' if long_step else 'burst'} of {peak_src}: kind::i8 issues at twice the bf16 rate; "
-                                      "kernel_ms from instrumented calls after the timed region (a synchronisation follows each phase, so the "
-                                      "clock recovers a little: the sum of the phases is below ms_per_step)",
+                                      "kernel_ms: " + phase_how,
                        "algorithmic_ops": "2*N*m*n*k int8 ops per launch"}
     enc_bytes = (8.0 * (m * k + k * n) * 2 + N * (m * k + k * n)) / world  # two passes over fp64 inputs + int8 slices out
     scal_ms = phase[0] / psteps / 1e6

@@ -61,7 +61,9 @@ enum {
     GEMMUL8_FLAG_HOST_SERIAL    = 1u << 9, /* gemm_host: copy in, compute, copy out in series (no wavefront) */
     GEMMUL8_FLAG_STRIPS         = 1u << 10, /* gemm: column-strip pipeline on three streams (measured slower) */
     GEMMUL8_FLAG_ONLY_SCALE_A   = 1u << 11, /* real types: shifts + residues of A only, then return (B may still be in flight) */
-    GEMMUL8_FLAG_SKIP_SCALE_A   = 1u << 12  /* real types: A's shifts + residues are already in `work` (previous flag)        */
+    GEMMUL8_FLAG_SKIP_SCALE_A   = 1u << 12, /* real types: A's shifts + residues are already in `work` (previous flag)        */
+    GEMMUL8_FLAG_PHASE_LOG      = 1u << 13  /* record the phase boundaries as events WITHOUT synchronising; the times of all such
+                                               calls of this host thread are summed by gemmul8_b200_phase_log_collect()      */
 };
 
 /* Arguments of one gemm call, in the reference's argument order (gemmul8.hpp:30-47). */
@@ -149,6 +151,10 @@ int gemmul8_b200_product_i32(const gemmul8_b200_args *args, unsigned j, int32_t 
 /* Constant tables (moduli, CRT weights, ...) for host-side tooling; row = num_moduli - 2. */
 int gemmul8_b200_modulus(unsigned j);                /* m_j, j in 0..19 */
 double gemmul8_b200_crt_weight(unsigned num_moduli, unsigned j, int part /*0=single,1=hi,2=lo*/);
+
+/* Sum of the phase times (ns, same slots as timers_ns) of every GEMMUL8_FLAG_PHASE_LOG call this host thread has made
+ * since the last collect, and how many calls that was.  Synchronises on the recorded events. */
+int gemmul8_b200_phase_log_collect(double timers_ns[4], unsigned *calls);
 
 /* Number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches). */
 unsigned long long gemmul8_b200_launch_count(void);

@@ -22,13 +22,13 @@ REAL_DEFAULT, COMPLEX_BIG_MATRIX_ENCODE, COMPLEX_CLASSIC_MULT, COMPLEX_KARATSUBA
 OP_N, OP_T, OP_C = 0, 1, 2
 F32, F64, C32, C64 = 0, 1, 2, 3
 FLAG_TIMERS, FLAG_STAGE_SCALING, FLAG_STAGE_RESIDUES, FLAG_FUSED_CRT, FLAG_GEMM_SIMT, FLAG_HOST_SERIAL, FLAG_STRIPS = 1, 1 << 4, 1 << 5, 1 << 6, 1 << 8, 1 << 9, 1 << 10
-FLAG_ONLY_SCALE_A, FLAG_SKIP_SCALE_A = 1 << 11, 1 << 12
+FLAG_ONLY_SCALE_A, FLAG_SKIP_SCALE_A, FLAG_PHASE_LOG = 1 << 11, 1 << 12, 1 << 13
 
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",
     "gemmul8_b200_gemm_host", "gemmul8_b200_gemm_part",
     "gemmul8_b200_worksize_blocked", "gemmul8_b200_plan_blocks", "gemmul8_b200_gemm_blocked", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
-    "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
+    "gemmul8_b200_phase_log_collect", "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
 )
 
 
@@ -97,6 +97,8 @@ def lib():
         L.gemmul8_b200_modulus.argtypes = [C.c_uint]
         L.gemmul8_b200_crt_weight.restype = C.c_double
         L.gemmul8_b200_crt_weight.argtypes = [C.c_uint, C.c_uint, C.c_int]
+        L.gemmul8_b200_phase_log_collect.restype = C.c_int
+        L.gemmul8_b200_phase_log_collect.argtypes = [C.POINTER(C.c_double * 4), C.POINTER(C.c_uint)]
         L.gemmul8_b200_launch_count.restype = C.c_ulonglong
         L.gemmul8_b200_last_error.restype = C.c_char_p
         L.gemmul8_b200_version.restype = C.c_char_p
@@ -282,6 +284,13 @@ def work_views_complex(work, L, num_moduli, m, n, k, computeType):
     v["sftA"] = work[L.off_sftA:L.off_sftA + 2 * m].view(torch.int16)
     v["sftB"] = work[L.off_sftB:L.off_sftB + 2 * n].view(torch.int16)
     return v
+
+
+def phase_log_collect():
+    """(phase times in ns summed over the FLAG_PHASE_LOG calls since the last collect, number of calls)."""
+    t, n = (C.c_double * 4)(), C.c_uint()
+    _check(lib().gemmul8_b200_phase_log_collect(C.byref(t), C.byref(n)))
+    return list(t), n.value
 
 
 def launch_count():

@@ -94,23 +94,60 @@ int check_args(const gemmul8_b200_args *a) {
     return GEMMUL8_OK;
 }
 
+// Phase boundaries as CUDA events on the caller's stream.
+//   GEMMUL8_FLAG_TIMERS   : the call synchronises on its last event and fills timers_ns (the reference's behaviour)
+//   GEMMUL8_FLAG_PHASE_LOG: nothing synchronises; the events go to a per-thread log that
+//                           gemmul8_b200_phase_log_collect() reads later (bench.py: phase times measured INSIDE the
+//                           timed region, with no host wait between or after the calls)
+struct PhaseLog {
+    struct Entry { cudaEvent_t ev[5]; int n; };
+    std::vector<Entry> entries;
+    std::vector<cudaEvent_t> pool;   // recycled events of device `dev` (an event belongs to the device it was created on)
+    int dev = -1;
+    cudaEvent_t get() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != dev) {
+            for (auto e : pool) cudaEventDestroy(e);
+            pool.clear();
+            dev = cur;
+        }
+        cudaEvent_t e = nullptr;
+        if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+thread_local PhaseLog g_phase_log;
+
 struct PhaseTimer {
-    bool on; cudaStream_t st; cudaEvent_t ev[5]; int n = 0;
-    PhaseTimer(bool enable, cudaStream_t s) : on(enable), st(s) {
-        if (on) for (auto &e : ev) cudaEventCreate(&e);
+    bool on, log; cudaStream_t st; cudaEvent_t ev[5]; int n = 0;
+    PhaseTimer(unsigned flags, cudaStream_t s)
+        : on((flags & (GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_PHASE_LOG)) != 0), log((flags & GEMMUL8_FLAG_PHASE_LOG) != 0), st(s) {
+        if (on) for (auto &e : ev) e = g_phase_log.get();
     }
     void mark() { if (on) cudaEventRecord(ev[n++], st); }
-    void finish(double *out_ns) {
-        if (!on) return;
-        cudaEventSynchronize(ev[n - 1]);
-        // marks: 0 start, 1 after scaling, 2 after gemm(+residues), 3 after crt
+    // marks: 0 start, 1 after scaling, 2 after gemm(+residues), 3 after crt
+    static void spans(cudaEvent_t *ev, int n, double *out_ns) {
         float ms;
         const int slot[3] = {0, 1, 3};
         for (int i = 0; i + 1 < n && i < 3; ++i) {
             cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-            out_ns[slot[i]] = (double)ms * 1e6;
+            out_ns[slot[i]] += (double)ms * 1e6;
         }
-        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    void finish(double *out_ns) {
+        if (!on) return;
+        if (log) {
+            PhaseLog::Entry e;
+            for (int i = 0; i < 5; ++i) e.ev[i] = ev[i];
+            e.n = n;
+            g_phase_log.entries.push_back(e);
+            return;
+        }
+        cudaEventSynchronize(ev[n - 1]);
+        spans(ev, n, out_ns);
+        for (auto &e : ev) g_phase_log.pool.push_back(e);
     }
 };
 
@@ -249,7 +286,7 @@ int gemm_real(gemmul8_b200_args *a) {
         return gemm_real_strips(a, L, strips);
     }
 
-    PhaseTimer timer((a->flags & GEMMUL8_FLAG_TIMERS) != 0, st);
+    PhaseTimer timer(a->flags, st);
     timer.mark();
 
     // ---------------- phase 0: scaling ----------------
@@ -351,7 +388,7 @@ int gemm_complex(gemmul8_b200_args *a) {
     tB.layout = big ? 2 : 0; tB.out_re = B_re; tB.out_im = big ? nullptr : B_im; tB.ld8i = L.lda8i; tB.inc = L.sizeB; tB.k = k; tB.nvec = n;
     const size_t rowsA = big ? 2 * m : m;   // rows of the int8 A operand
 
-    PhaseTimer timer((a->flags & GEMMUL8_FLAG_TIMERS) != 0, st);
+    PhaseTimer timer(a->flags, st);
     timer.mark();
 
     // ---------------- phase 0: scaling ----------------
@@ -930,6 +967,21 @@ int gemmul8_b200_product_i32(const gemmul8_b200_args *a, unsigned j, int32_t *C3
     gp.C32i = C32i_out; gp.ldc32i = L.m_pad;
     auto gemm = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
     OZ_CUDA(gemm(gp, oz::EPI_INT32, static_cast<cudaStream_t>(a->stream)), "int32 product");
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_phase_log_collect(double timers_ns[4], unsigned *calls) {
+    PhaseLog &L = g_phase_log;
+    if (timers_ns) for (int i = 0; i < 4; ++i) timers_ns[i] = 0.0;
+    if (calls) *calls = (unsigned)L.entries.size();
+    for (auto &e : L.entries) {
+        if (e.n > 0 && cudaEventSynchronize(e.ev[e.n - 1]) != cudaSuccess) return fail(GEMMUL8_ERR_CUDA, "phase log: event synchronise failed");
+        double t[4] = {0, 0, 0, 0};
+        PhaseTimer::spans(e.ev, e.n, t);
+        if (timers_ns) for (int i = 0; i < 4; ++i) timers_ns[i] += t[i];
+        for (auto &ev : e.ev) L.pool.push_back(ev);
+    }
+    L.entries.clear();
     return GEMMUL8_OK;
 }
 

@@ -396,6 +396,26 @@ def test_cuda_graph_capture_and_replay(g):
     assert torch.equal(C, want2)
 
 
+def test_phase_log_records_without_synchronising(g):
+    """FLAG_PHASE_LOG: phase boundaries go to a per-thread event log (no host wait); collect() sums them later."""
+    torch = torch_()
+    m, n, k, N = 1024, 768, 2048, 14
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=3)
+    want, _ = run_ours(g, m, n, k, N, True, A, B)
+    g.phase_log_collect()
+    work = torch.zeros(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+    C = torch.zeros_like(want)
+    for _ in range(5):
+        t = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=g.FLAG_PHASE_LOG)
+        assert t == [0.0] * 4                       # nothing was waited for
+    ph, calls = g.phase_log_collect()
+    assert calls == 5 and ph[0] > 0 and ph[1] > 0 and ph[2] == 0 and ph[3] > 0
+    assert g.phase_log_collect() == ([0.0] * 4, 0)
+    assert torch.equal(C, want)
+    t = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work, flags=g.FLAG_TIMERS)   # the synchronising flavour still works
+    assert t[1] > 0 and 0.2 < t[1] / (ph[1] / 5) < 5.0
+
+
 def test_strip_pipeline_equals_default(g):
     """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
     torch = torch_()
