@@ -94,28 +94,32 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
         return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
                         num_moduli, fastmode, work, flags=flags)
     # The row and the column communicator are different NCCL communicators with their own streams, so the
-    # A and B exchanges run at the same time; A travels as two row halves, and everything that depends only
-    # on what has arrived is computed while the rest is still in flight:
-    #     B panel, A rows [0, h)  ->  scale B, scale A_0, C[0:h, :]      (A rows [h, m) still arriving)
-    #     A rows [h, m)           ->  scale A_1, C[h:m, :]
-    h = (m_loc // 2) // 256 * 256
-    if grid.Q == 1 or h == 0:
-        a_panel, parts_a = a_slice, [(0, m_loc, None)]
+    # A and B exchanges run at the same time; A travels as up to four row pieces, and everything that depends
+    # only on what has arrived is computed while the rest is still in flight:
+    #     A rows of piece 0, B panel  ->  scale A_0, scale B, C[piece 0, :]      (later pieces still arriving)
+    #     A rows of piece i           ->  scale A_i, C[piece i, :]
+    # A piece is gathered into its own (k, rows) tensor -- a column-major rows x k matrix with leading dimension
+    # `rows` -- and the block-wise entry reads it in place: the args of piece i carry lda = rows and an A pointer
+    # moved back by r0 elements, so that "row r of the full panel" (r0 <= r < r1, all that SCALE_A touches)
+    # addresses row r - r0 of the piece.  No copy into a contiguous panel.
+    import ctypes
+    pieces = row_pieces(m_loc, 4 if grid.Q > 1 else 1)
+    es = a_slice.element_size()
+    pending = []
+    if grid.Q == 1:
+        pending.append((0, m_loc, None, a_slice))
     else:
-        a_panel = torch.empty((k, m_loc), dtype=a_slice.dtype, device=a_slice.device)
-        parts_a = []
-        for (r0, r1) in ((0, h), (h, m_loc)):
-            piece = torch.empty((k, r1 - r0), dtype=a_slice.dtype, device=a_slice.device)     # (k, rows) = column-major rows x k
+        for (r0, r1) in pieces:
+            piece = torch.empty((k, r1 - r0), dtype=a_slice.dtype, device=a_slice.device)
             w = dist.all_gather_into_tensor(piece, a_slice[:, r0:r1].contiguous(), group=grid.row_group, async_op=True)
-            parts_a.append((r0, r1, (w, piece)))
+            pending.append((r0, r1, w, piece))
     b_panel, wb = grid.gather_b_panel(b_slice, n_loc, k, async_op=True)
-    args = pkg.make_args(0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc, num_moduli, fastmode, work)
     first = True
-    for (r0, r1, pending) in parts_a:
-        if pending is not None:
-            w, piece = pending
+    for (r0, r1, w, piece) in pending:
+        args = pkg.make_args(0, 0, m_loc, n_loc, k, alpha, piece, r1 - r0, b_panel, k, beta, c_block, m_loc, num_moduli, fastmode, work)
+        args.A = ctypes.c_void_p(piece.data_ptr() - r0 * es)
+        if w is not None:
             w.wait()                                          # the compute stream waits; the host does not block
-            a_panel[:, r0:r1].copy_(piece)                    # place the rows in the panel (device copy, ~1% of the step)
         pkg.gemm_part(args, pkg.PART_SCALE_A, r0, r1, 0, 0)
         if first:
             if wb is not None:
@@ -124,3 +128,11 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
             first = False
         pkg.gemm_part(args, pkg.PART_PRODUCT, r0, r1, 0, n_loc)
     return [0.0, 0.0, 0.0, 0.0]
+
+
+def row_pieces(m_loc, want):
+    """Up to `want` row ranges of [0, m_loc) whose starts are multiples of 256 (whole GEMM tiles)."""
+    tiles = (m_loc + 255) // 256
+    n = max(1, min(want, tiles))
+    cuts = sorted({min(m_loc, (tiles * i // n) * 256) for i in range(n)} | {m_loc})
+    return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]

@@ -30,6 +30,16 @@ def test_grid_shapes():
         assert len(seen) == world
 
 
+def test_row_pieces_cover_the_block_on_tile_boundaries():
+    d = _dmod()
+    for m_loc in (1, 255, 256, 257, 300, 777, 1000, 4096, 16384, 32768, 33000):
+        for want in (1, 2, 4, 8):
+            pcs = d.row_pieces(m_loc, want)
+            assert pcs[0][0] == 0 and pcs[-1][1] == m_loc and len(pcs) <= want
+            assert all(a[1] == b[0] for a, b in zip(pcs, pcs[1:]))
+            assert all(r0 % 256 == 0 and r1 > r0 for r0, r1 in pcs)
+
+
 def test_ownership_partitions_cover_panels():
     d = _dmod()
     m, n, k = 64, 96, 48
