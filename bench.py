@@ -241,7 +241,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    live_phases = not multi and not args.lowmem
+    live_phases = not args.lowmem and fast
     if live_phases:
         g.phase_log_collect()       # empty the log
     for _ in range(args.steps):
@@ -263,6 +263,9 @@ def main():
         phase_how = ("instrumented calls after the timed region (a synchronisation follows each call, so the clock recovers a little: "
                      "the sum of the phases is below ms_per_step)")
     barrier()
+    if multi and live_phases:
+        # scale / product steps of the pipelined exchange are logged one by one: bring the counts back to "per step"
+        psteps = args.steps
     if multi:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -285,10 +288,14 @@ def main():
                        "peak_source": f"2 x bf16 {'sustained' if long_step else 'burst'} of {peak_src}: kind::i8 issues at twice the bf16 rate; "
                                       "kernel_ms: " + phase_how,
                        "algorithmic_ops": "2*N*m*n*k int8 ops per launch"}
-    enc_bytes = (8.0 * (m * k + k * n) * 2 + N * (m * k + k * n)) / world  # two passes over fp64 inputs + int8 slices out
+    ml, nl = (m_loc, n_loc) if multi else (m, n)
+    enc_bytes = (8.0 * 2 + N) * (ml * k + k * nl)   # per GPU: two passes over its fp64 panels + their int8 slices out
     scal_ms = phase[0] / psteps / 1e6
     out["phases_ms"] = {"scaling": scal_ms, "int8_gemm_fused_residue": gemm_ms, "crt_inverse_scaling": phase[3] / psteps / 1e6,
                         "scaling_GBps": enc_bytes / (scal_ms * 1e-3) / 1e9 if scal_ms > 0 else None, "hbm_peak_GBps": hbm}
+    if multi and live_phases:
+        out["phases_ms"]["exposed_exchange_and_gaps"] = ms_step - (scal_ms + gemm_ms + phase[3] / psteps / 1e6)
+        out["phases_ms"]["note"] = "rank 0; kernels timed by events inside the timed region, the rest of the step is waiting for panel pieces"
     out["config"] = {"workload": f"DGEMM emulation m={m} n={n} k={k}, {N} moduli, {'fast' if fast else 'accurate'} mode, phi={PHI}, ops N/N, alpha=1 beta=0",
                      "parallelism": f"{world} GPU(s)" + (f", {grid.P}x{grid.Q} C-block grid, NCCL all-gather of FP64 panels" if multi else ""),
                      "l2": f"inputs ({8 * (m * k + k * n) / world / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no explicit flush"}

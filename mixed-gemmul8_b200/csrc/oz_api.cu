@@ -532,6 +532,9 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
     const int ref_width  = oz::ref_reduce_width(a->dtype_A, a->dtype_B, a->dtype_C);
     const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
     const size_t esA = elem_size(a->dtype_A), esB = elem_size(a->dtype_B), esC = elem_size(a->dtype_C);
+    for (double &t : a->timers_ns) t = 0.0;
+    PhaseTimer timer(a->flags, st);   // GEMMUL8_FLAG_TIMERS / _PHASE_LOG: the same four slots as gemm()
+    timer.mark();
     if ((parts & GEMMUL8_PART_SCALE_A) && row1 > row0 && k > 0) {
         const uint8_t *Ax = static_cast<const uint8_t *>(a->A) + (a_strided ? row0 : row0 * a->lda) * esA;
         rc = scale_operand(a->dtype_A, a_strided, Ax, a->lda, row1 - row0, k, ref_width, l2, N, A8i + row0 * L.lda8i, L.lda8i, L.sizeA,
@@ -552,11 +555,16 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
         gp.A8i = A8i + row0 * L.lda8i; gp.rowsA = row1 - row0;
         gp.B8i = B8i + col0 * L.lda8i; gp.rowsB = col1 - col0;
         gp.C8u = C8u + col0 * L.m_pad + row0;
+        gp.share_sm = true;   // a block-wise caller overlaps this product with transfers of the next pieces
+        timer.mark();
         OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+        timer.mark();
         OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, row1 - row0, col1 - col0, gp.C8u, L.m_pad, L.sizeC,
                                static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, a->ldc, sftA + row0, sftB + col0, a->alpha, a->beta,
                                st), "crt");
     }
+    timer.mark();
+    timer.finish(a->timers_ns);
     return GEMMUL8_OK;
 }
 

@@ -991,7 +991,7 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     const char *sk = getenv("OZ_PAIR_SKEW");
     a.debug_skew = sk ? (uint32_t)atoi(sk) : 0u;
     const char *se = getenv("OZ_PAIR_STAGES");   // tuning knob
-    const int stages = se ? atoi(se) : PAIR_STAGES;
+    const int stages = se ? atoi(se) : p.share_sm ? 4 : PAIR_STAGES;
     auto kern = stages == 4 ? oz_gemm_pair_kernel<RMW, 4> : stages == 5 ? oz_gemm_pair_kernel<RMW, 5> : oz_gemm_pair_kernel<RMW, 6>;
     const int smem_bytes = pair_smem_total(stages == 4 ? 4 : stages == 5 ? 5 : 6);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

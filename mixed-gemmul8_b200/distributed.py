@@ -87,7 +87,7 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
 
     a_slice / b_slice are this rank's pre-exchange pieces (see BlockGrid); returns the phase timers."""
     m_loc, n_loc = grid.block_dims(m, n)
-    overlap = fastmode and a_slice.is_cuda and flags == 0 and not a_slice.is_complex()
+    overlap = fastmode and a_slice.is_cuda and (flags & ~pkg.FLAG_PHASE_LOG) == 0 and not a_slice.is_complex()
     if not overlap:
         a_panel = grid.gather_a_panel(a_slice, m_loc, k)
         b_panel = grid.gather_b_panel(b_slice, n_loc, k)
@@ -116,7 +116,8 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
     b_panel, wb = grid.gather_b_panel(b_slice, n_loc, k, async_op=True)
     first = True
     for (r0, r1, w, piece) in pending:
-        args = pkg.make_args(0, 0, m_loc, n_loc, k, alpha, piece, r1 - r0, b_panel, k, beta, c_block, m_loc, num_moduli, fastmode, work)
+        args = pkg.make_args(0, 0, m_loc, n_loc, k, alpha, piece, r1 - r0, b_panel, k, beta, c_block, m_loc, num_moduli, fastmode, work,
+                             flags=flags)
         args.A = ctypes.c_void_p(piece.data_ptr() - r0 * es)
         if w is not None:
             w.wait()                                          # the compute stream waits; the host does not block
