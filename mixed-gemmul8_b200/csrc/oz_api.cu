@@ -241,6 +241,7 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.rowsA = m; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
     gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    gp.share_sm = true;   // encoder / CRT blocks of the side streams must fit beside the persistent GEMM CTAs
     for (int j = 0; j < strips; ++j) {
         const size_t c0 = cb[j], c1 = cb[j + 1];
         OZ_CUDA(cudaStreamWaitEvent(st, S.evB[j], 0), "stream wait");
