@@ -490,6 +490,10 @@ int gemmul8_b200_gemm(gemmul8_b200_args *a) {
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
         return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (a->k == 0) {   // empty product: C = beta * C (the reference launches its kernels on empty operands: undefined)
+        OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, static_cast<cudaStream_t>(a->stream)), "scale C");
+        return GEMMUL8_OK;
+    }
     if (is_complex(a->dtype_C)) {
         if (a->k > (size_t(1) << 16)) return fail(GEMMUL8_ERR_ARGUMENT, "complex types: k must be <= 2^16 (int32 accumulation)");
         return gemm_complex(a);
@@ -548,7 +552,10 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
                            sftB + col0, true, st);
         if (rc) return rc;
     }
-    if ((parts & GEMMUL8_PART_PRODUCT) && row1 > row0 && col1 > col0) {
+    if ((parts & GEMMUL8_PART_PRODUCT) && row1 > row0 && col1 > col0 && k == 0) {
+        OZ_CUDA(oz::launch_scale_c(a->dtype_C, row1 - row0, col1 - col0, static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, a->ldc,
+                                   a->beta, st), "scale C");
+    } else if ((parts & GEMMUL8_PART_PRODUCT) && row1 > row0 && col1 > col0) {
         const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;
         oz::GemmProblem gp{};
         gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
@@ -785,6 +792,10 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
     int dev_count = 0;
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
         return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (a->k == 0) {
+        OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, static_cast<cudaStream_t>(a->stream)), "scale C");
+        return GEMMUL8_OK;
+    }
     return gemm_blocked_real(a, P);
 }
 

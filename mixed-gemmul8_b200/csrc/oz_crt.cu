@@ -102,6 +102,39 @@ cudaError_t run_crt(bool split, unsigned N, size_t m, size_t n, const uint8_t *C
 
 }  // namespace
 
+namespace {
+// k == 0: the product is empty, C = beta * C (BLAS: C is not read when beta == 0)
+template <typename T>
+__global__ void scale_c_kernel(size_t m, size_t n, T *__restrict__ C, size_t ldc, T beta_re, T beta_im, bool cplx) {
+    const size_t w = cplx ? 2 * m : m;                 // scalars per column
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (i >= w) return;
+    T *c = C + col * (cplx ? 2 * ldc : ldc);
+    if (beta_re == T(0) && beta_im == T(0)) { c[i] = T(0); return; }
+    if (!cplx) { c[i] = beta_re * c[i]; return; }
+    if (i & 1) return;                                 // even lanes own (re, im)
+    const T re = c[i], im = c[i + 1];
+    c[i]     = beta_re * re - beta_im * im;
+    c[i + 1] = beta_re * im + beta_im * re;
+}
+}  // namespace
+
+cudaError_t launch_scale_c(int dtype_C, size_t m, size_t n, void *C, size_t ldc, const void *beta_host, cudaStream_t st) {
+    if (m == 0 || n == 0) return cudaSuccess;
+    if (n > 65535) return cudaErrorInvalidValue;
+    const bool cplx = dtype_C == DT_C32 || dtype_C == DT_C64;
+    dim3 grid((unsigned)(((cplx ? 2 * m : m) + 255) / 256), (unsigned)n);
+    if (dtype_C == DT_F64 || dtype_C == DT_C64) {
+        const double *b = static_cast<const double *>(beta_host);
+        scale_c_kernel<double><<<grid, 256, 0, st>>>(m, n, static_cast<double *>(C), ldc, b[0], cplx ? b[1] : 0.0, cplx);
+    } else {
+        const float *b = static_cast<const float *>(beta_host);
+        scale_c_kernel<float><<<grid, 256, 0, st>>>(m, n, static_cast<float *>(C), ldc, b[0], cplx ? b[1] : 0.f, cplx);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_crt(int dtype_C, bool split_weights, unsigned num_moduli, size_t m, size_t n, const uint8_t *C8u,
                        size_t ldc8u, size_t sizeC, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB,
                        const void *alpha_host, const void *beta_host, cudaStream_t st) {

@@ -396,6 +396,42 @@ def test_cuda_graph_capture_and_replay(g):
     assert torch.equal(C, want2)
 
 
+@pytest.mark.parametrize("dt", ["float64", "float32", "complex128"])
+def test_empty_inner_dimension(g, dt):
+    """k == 0: the product is empty, C = beta * C (zeros for beta == 0, even over NaNs) -- through gemm, the low-memory
+    call and the block-wise entry.  m == 0 or n == 0: nothing is touched."""
+    torch = torch_()
+    t = getattr(torch, dt)
+    m, n, N = 300, 200, 14
+    ct = g.COMPLEX_KARATSUBA_MULT if t.is_complex else g.REAL_DEFAULT
+    A = torch.zeros(16, dtype=t, device="cuda")
+    C0 = g.phi_matrix(m, n, 1.0, t, seed=5)
+    work = torch.zeros(max(g.workSize(m, n, 0, N, ct), 4096), dtype=torch.uint8, device="cuda")
+    beta = (0.5 - 2.0j) if t.is_complex else -1.5
+    C = C0.clone()
+    g.gemm(None, 0, 0, m, n, 0, 1.0, A, m, A, 1, beta, C, m, N, True, work, computeType=ct)
+    torch.cuda.synchronize()
+    assert torch.allclose(C, beta * C0, rtol=1e-6 if dt == "float32" else 1e-12, atol=1e-12)
+    C = torch.full_like(C0, float("nan"))
+    g.gemm(None, 0, 0, m, n, 0, 1.0, A, m, A, 1, 0.0, C, m, N, False, work, computeType=ct)
+    torch.cuda.synchronize()
+    assert bool((C == 0).all())
+    if not t.is_complex:
+        C = C0.clone()
+        g.gemm_blocked(None, 0, 0, m, n, 0, 1.0, A, m, A, 1, beta, C, m, N, True, work, 256, 256)
+        args = g.make_args(0, 0, m, n, 0, 1.0, A, m, A, 1, beta, C, m, N, True, work)
+        C2 = C0.clone()
+        args.C = C2.data_ptr()
+        g.gemm_part(args, g.PART_SCALE_A | g.PART_SCALE_B | g.PART_PRODUCT, 0, m, 0, n)
+        torch.cuda.synchronize()
+        assert torch.equal(C, beta * C0) and torch.equal(C2, beta * C0)
+    C = C0.clone()
+    g.gemm(None, 0, 0, 0, n, 5, 1.0, A, 1, A, 5, 0.0, C, m, N, True, work, computeType=ct)
+    g.gemm(None, 0, 0, m, 0, 5, 1.0, A, m, A, 5, 0.0, C, m, N, True, work, computeType=ct)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(C) if t.is_complex else C, torch.view_as_real(C0) if t.is_complex else C0)
+
+
 def test_phase_log_records_without_synchronising(g):
     """FLAG_PHASE_LOG: phase boundaries go to a per-thread event log (no host wait); collect() sums them later."""
     torch = torch_()
