@@ -49,9 +49,21 @@ __global__ void __launch_bounds__(256) crt_kernel(size_t m, size_t n, const uint
             for (int e = 0; e < 4; ++e) sa[e] = sftA[row0 + e];
         }
         T out[4];
+        int ex[4];
+        bool normal = true;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            out[e] = combine<T>(mode, alpha, beta, cast_out<T>(scale_pow2(crt_finish<SPLIT>(N, s1[e], s2[e]), sa[e] + sb)), cptr + e);
+        for (int e = 0; e < 4; ++e) { ex[e] = sa[e] + sb; normal &= (unsigned)(ex[e] + 1022) <= 2045u; }
+        if (mode == AB_10 && normal) {
+            // the common case (alpha = 1, beta = 0, every 2^e a normal number) without the per-element mode dispatch
+            // and scalbn fallbacks: one exact multiply by a constructed power of two
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                out[e] = cast_out<T>(crt_finish<SPLIT>(N, s1[e], s2[e]) * __hiloint2double((1023 + ex[e]) << 20, 0));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                out[e] = combine<T>(mode, alpha, beta, cast_out<T>(scale_pow2(crt_finish<SPLIT>(N, s1[e], s2[e]), ex[e])), cptr + e);
+        }
         if ((reinterpret_cast<uintptr_t>(cptr) & (4 * sizeof(T) - 1)) == 0) {
             if constexpr (sizeof(T) == 8) {
                 reinterpret_cast<double2 *>(cptr)[0] = make_double2(out[0], out[1]);
