@@ -124,6 +124,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same, with the loaded registers as in/out operands: every use of v is ordered after the wait by data flow, so
+// another tcgen05.ld may be in flight (software-pipelined epilogue) without relying on instruction order alone
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 
 // K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups (1024 B) are the
 // stride dimension; descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
@@ -555,7 +564,10 @@ constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_SMEM_A = BLOCK_M * BLOCK_K;          // 128 rows of A
 constexpr int PAIR_SMEM_B = 128 * BLOCK_K;              // 128 of the tile's 256 columns of B
 constexpr int PAIR_STAGE  = PAIR_SMEM_A + PAIR_SMEM_B;  // 32 KiB per CTA and stage
-constexpr int pair_smem_total(int stages) { return stages * PAIR_STAGE + SMEM_BARRIERS + SMEM_SCRATCH + 1024; }
+constexpr int PAIR_EPI_WARPS = 16;                      // 4 per TMEM lane quarter, 64 of the tile's 256 columns each
+constexpr int PAIR_THREADS   = (4 + PAIR_EPI_WARPS) * 32;
+constexpr int PAIR_SCRATCH   = PAIR_EPI_WARPS * 32 * 5 * 4;
+constexpr int pair_smem_total(int stages) { return stages * PAIR_STAGE + SMEM_BARRIERS + PAIR_SCRATCH + 1024; }
 constexpr int PAIR_BAND = 8;                            // 256-row tiles per scheduling band
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -574,6 +586,22 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// The "accumulator drained" signal hands over tensor memory, not data in global or shared memory: the tcgen05.ld of
+// this warp have completed (tcgen05.wait::ld) and are fenced (tcgen05.fence::before_thread_sync) when it is sent.  A
+// release at cluster scope would also wait for the warp's residue STOREs to be acknowledged (MEMBAR.GPU + ERRBAR,
+// 8 % of the epilogue's time at k = 2048) before the MMA warp may reuse the buffer.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// x mod m in [0, m) for |x| <= 2^17 * 127^2 (every modulus but 256 has |residue| <= 127, k <= 2^17): shift x by a
+// multiple of m into the unsigned range, q = umulhi(x', floor(2^32 / m)) is floor(x' / m) or one less, ONE correction
+constexpr uint32_t kMaxAbsProduct = 2114060288u;   // 2^17 * 127^2
+__device__ __forceinline__ uint32_t reduce_mod_u(int32_t x, uint32_t m, uint32_t inv, uint32_t off) {
+    const uint32_t xu = (uint32_t)x + off;
+    uint32_t r = xu - __umulhi(xu, inv) * m;
+    r -= (r >= m) ? m : 0u;
+    return r;
 }
 // TMA load into this CTA's shared memory; the transaction bytes land on the barrier at `bar_cluster_addr`
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
@@ -624,7 +652,7 @@ struct PairArgs {
 };
 
 template <bool RMW, int NSTAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PairArgs args) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -658,7 +686,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }   // 8 epilogue warps x 2 CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * PAIR_EPI_WARPS); }   // epilogue warps of both CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -715,49 +743,64 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
-        const int q = warp & 3;
+        // 16 warps: warp & 3 = TMEM lane quarter (32 rows), (warp - 4) >> 2 = 64-column group, 4 chunks of 16 columns.
+        // With short k the kernel is bound by this loop, not by the MMA (k = 2048: 8 warps kept the tensor pipe at
+        // 49 %), so it is built for issue slots: unsigned Barrett with one correction, the modulus-256 case hoisted,
+        // interior tiles without bounds checks, running store pointers.
+        const int q = warp & 3, colgroup = (warp - 4) >> 2;
         const int rg = lane & 7, cg = lane >> 3;
         uint32_t *scr = reinterpret_cast<uint32_t *>(smem_raw + (bar_base + SMEM_BARRIERS - smem_u32(smem_raw))) + (warp - 4) * 160;
-        constexpr int NCH = 8;
-        const int ch0     = warp >= 8 ? 8 : 0;
+        constexpr int NCH = 4;
+        const int ch0     = NCH * colgroup;
+        const size_t ld   = args.ldc8u;
         uint32_t tm, tn, j, it = 0;
         for (uint32_t item = pair; item < total; item += npairs, ++it) {
             args.sched.decode(item, tm, tn, j);
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const uint32_t col0 = tn * BLOCK_N;
-            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+            const uint32_t col0 = tn * BLOCK_N + 16 * ch0 + 4 * cg;     // this lane's first column
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16) + 16 * ch0;
             const uint32_t row4 = tm * 256 + rank * 128 + q * 32 + 4 * rg;
             const bool rows4_ok = row4 < args.rows_store;
-            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4;
-            uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4;
+            const bool interior = (tm * 256 + 256 <= args.rows_store) && (tn * BLOCK_N + BLOCK_N <= args.rowsB);
+            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4 + (size_t)col0 * ld;
+            uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4 + (size_t)col0 * ld;
             uint32_t old[RMW ? 4 * NCH : 1];
             if constexpr (RMW) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        const uint32_t col = col0 + 16 * (ch0 + c) + 4 * cg + jj;
-                        old[4 * c + jj] = (rows4_ok && col < args.rowsB) ? __ldcg(reinterpret_cast<const uint32_t *>(out4 + (size_t)col * args.ldc8u)) : 0u;
+                        const uint32_t col = col0 + 16 * c + jj;
+                        old[4 * c + jj] = (rows4_ok && col < args.rowsB) ? __ldcg(reinterpret_cast<const uint32_t *>(out4 + (size_t)(16 * c + jj) * ld)) : 0u;
                     }
             }
+            const uint32_t mj = args.first_modulus + j;
+            const uint32_t m  = (uint32_t)dev_tab::OZ_MOD[mj];
+            const uint32_t inv = (uint32_t)(4294967296ull / m);
+            const uint32_t off = m * ((kMaxAbsProduct + m - 1) / m);
+            const int rc       = args.combine;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
-            const uint32_t mj = args.first_modulus + j;
-            const int32_t m   = dev_tab::OZ_MOD[mj];
-            const int32_t inv = (int32_t)(4294967296ull / (uint32_t)m);
-            const int rc      = args.combine;
-#pragma unroll(RMW ? NCH : 1)
+#pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[16];
-                tmem_ld16(taddr + 16 * (ch0 + c), v);
-                tmem_ld_wait();
-                uint32_t r[16];
+                tmem_ld16(taddr + 16 * c, v);
+                tmem_ld_wait(v);
+                uint32_t pk[4];
+                if (mj == 0) {          // modulus 256: the low byte (the only product that may wrap)
 #pragma unroll
-                for (int e = 0; e < 16; ++e) r[e] = (mj == 0) ? (v[e] & 0xffu) : reduce_mod((int32_t)v[e], m, inv);
+                    for (int w = 0; w < 4; ++w)
+                        pk[w] = __byte_perm(__byte_perm(v[4 * w], v[4 * w + 1], 0x0040), __byte_perm(v[4 * w + 2], v[4 * w + 3], 0x0040), 0x5410);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = reduce_mod_u((int32_t)v[e], m, inv, off);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        pk[w] = __byte_perm(__byte_perm(v[4 * w], v[4 * w + 1], 0x0040), __byte_perm(v[4 * w + 2], v[4 * w + 3], 0x0040), 0x5410);
+                }
                 __syncwarp();
 #pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    scr[5 * lane + w] = r[4 * w] | (r[4 * w + 1] << 8) | (r[4 * w + 2] << 16) | (r[4 * w + 3] << 24);
+                for (int w = 0; w < 4; ++w) scr[5 * lane + w] = pk[w];
                 __syncwarp();
                 const uint32_t w0 = scr[5 * (4 * rg) + cg], w1 = scr[5 * (4 * rg + 1) + cg];
                 const uint32_t w2 = scr[5 * (4 * rg + 2) + cg], w3 = scr[5 * (4 * rg + 3) + cg];
@@ -765,24 +808,32 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
                 uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
                                  __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+                uint8_t *po = out4 + (size_t)(16 * c) * ld;
+                if constexpr (!RMW) {
+                    if (interior) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint32_t *>(po + (size_t)jj * ld) = o[jj];
+                        continue;
+                    }
+                }
                 if (rows4_ok) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        const uint32_t col = col0 + 16 * (ch0 + c) + 4 * cg + jj;
+                        const uint32_t col = col0 + 16 * c + jj;
                         if (col < args.rowsB) {
                             if constexpr (RMW) {
                                 uint32_t ax;
-                                o[jj] = combine_word(rc, o[jj], old[4 * c + jj], ax, m);
-                                if (rc == RC_KARATSUBA_F) *reinterpret_cast<uint32_t *>(aux4 + (size_t)col * args.ldc8u) = ax;
+                                o[jj] = combine_word(rc, o[jj], old[4 * c + jj], ax, (int32_t)m);
+                                if (rc == RC_KARATSUBA_F) *reinterpret_cast<uint32_t *>(aux4 + (size_t)(16 * c + jj) * ld) = ax;
                             }
-                            *reinterpret_cast<uint32_t *>(out4 + (size_t)col * args.ldc8u) = o[jj];
+                            *reinterpret_cast<uint32_t *>(po + (size_t)jj * ld) = o[jj];
                         }
                     }
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(acc), 0));   // tell the leader: this warp has drained the buffer
+            if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(tempty_bar(acc), 0));   // tell the leader: this warp has drained the buffer
         }
     }
 
@@ -1000,7 +1051,7 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     const uint32_t pairs = a.sched.total < max_pairs ? a.sched.total : max_pairs;
     const char *pm = getenv("OZ_PAIR_MAP");
     a.slot = (pairs == max_pairs && (uint32_t)sm_count() == 2 * max_pairs && !(pm && pm[0] == '0')) ? placement_slots() : nullptr;
-    kern<<<2 * pairs, NUM_THREADS, smem_bytes, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
+    kern<<<2 * pairs, PAIR_THREADS, smem_bytes, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
     count_launch();
     return cudaGetLastError();
 }
