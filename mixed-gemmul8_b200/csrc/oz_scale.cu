@@ -20,6 +20,8 @@
 #include "oz_common.cuh"
 #include "oz_residue.cuh"
 
+#include <cstdlib>
+
 namespace oz {
 namespace {
 
@@ -190,6 +192,65 @@ __global__ void __launch_bounds__(W) fast_shift_strided_kernel(const T *__restri
         R a = 0;
 #pragma unroll
         for (int g = 0; g < NW; ++g) a = fmax(a, s_amax[g][lane]);
+        const R s = ref_tree_lane0<R, NW>(&s_u[0][lane], 33);
+        out[vec] = (int16_t)(-fast_sft(a, s, log2M));
+    }
+}
+
+// The same with the 32 virtual threads of a virtual warp spread over 32 / VT real warps (VT accumulators per
+// thread): W / VT warps per 32 vectors instead of W / 32, i.e. 4x (VT = 8) the loads in flight when there are few
+// vectors -- 1024 ... 8192 rows give only 32 ... 256 CTAs, and the reference's order forbids splitting a vector's
+// chains along k.  The partial sums meet in shared memory, where warp g evaluates virtual warp g's tree as above.
+template <typename T, int W, int VT>
+__global__ void __launch_bounds__(W / VT * 32) fast_shift_strided_split_kernel(const T *__restrict__ X, size_t ld, size_t nvec,
+                                                                               size_t len, float log2M, int16_t *__restrict__ out) {
+    using R = typename Real<T>::type;
+    constexpr int NW = W / 32;            // virtual warps
+    constexpr int NWARP = W / VT;         // real warps
+    __shared__ R s_acc[W][32];            // [virtual thread][vector]
+    __shared__ R s_amax[NWARP][32];
+    __shared__ R s_u[NW][33];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t vec  = (size_t)blockIdx.x * 32 + lane;
+    const bool active = vec < nvec;
+    const T *__restrict__ p = X + (active ? vec : 0);
+
+    R acc[VT];
+#pragma unroll
+    for (int q = 0; q < VT; ++q) acc[q] = 0;
+    R amax = 0;
+    if (active) {
+        size_t base = (size_t)warp * VT;              // virtual threads [VT * warp, VT * warp + VT)
+        for (; base + VT <= len; base += W) {
+            const T *__restrict__ pb = p + base * ld;
+            T x[VT];
+#pragma unroll
+            for (int q = 0; q < VT; ++q) x[q] = pb[(size_t)q * ld];
+#pragma unroll
+            for (int q = 0; q < VT; ++q) accumulate<T, R>(x[q], amax, acc[q]);
+        }
+        if (base < len) {
+#pragma unroll
+            for (int q = 0; q < VT; ++q)
+                if (base + q < len) accumulate<T, R>(p[(base + q) * ld], amax, acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < VT; ++q) s_acc[warp * VT + q][lane] = acc[q];
+    s_amax[warp][lane] = amax;
+    __syncthreads();
+    if (warp < NW) {
+        R v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = s_acc[warp * 32 + i][lane];
+        s_u[warp][lane] = ref_tree_lane1(v);
+    }
+    __syncthreads();
+    if (warp == 0 && active) {
+        R a = 0;
+#pragma unroll
+        for (int g = 0; g < NWARP; ++g) a = fmax(a, s_amax[g][lane]);
         const R s = ref_tree_lane0<R, NW>(&s_u[0][lane], 33);
         out[vec] = (int16_t)(-fast_sft(a, s, log2M));
     }
@@ -417,6 +478,15 @@ cudaError_t run_fast_shifts(bool strided, const void *X, size_t ld, size_t nvec,
     using R = typename Real<T>::type;
     if (nvec == 0) return cudaSuccess;
     if (strided) {
+        static const int split_below = [] { const char *e = getenv("OZ_SHIFT_SPLIT_BELOW"); return e ? atoi(e) : 32768; }();
+        if constexpr (W == 128 && sizeof(R) <= 8 && !Real<T>::cplx) {
+            if (nvec < (size_t)split_below) {
+                fast_shift_strided_split_kernel<T, W, 8><<<(unsigned)((nvec + 31) / 32), W / 8 * 32, 0, st>>>(static_cast<const T *>(X), ld, nvec,
+                                                                                                            len, log2M, out);
+                count_launch();
+                return cudaGetLastError();
+            }
+        }
         fast_shift_strided_kernel<T, W><<<(unsigned)((nvec + 31) / 32), W, 0, st>>>(static_cast<const T *>(X), ld, nvec, len, log2M, out);
     } else {
         fast_shift_contig_kernel<T, W><<<(unsigned)nvec, W, 0, st>>>(static_cast<const T *>(X), ld, len, log2M, out);
