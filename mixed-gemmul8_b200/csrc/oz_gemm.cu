@@ -584,9 +584,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // The "accumulator drained" signal hands over tensor memory, not data in global or shared memory: the tcgen05.ld of
 // this warp have completed (tcgen05.wait::ld) and are fenced (tcgen05.fence::before_thread_sync) when it is sent.  A
 // release at cluster scope would also wait for the warp's residue STOREs to be acknowledged (MEMBAR.GPU + ERRBAR,

@@ -39,7 +39,9 @@ struct Config {
     unsigned moduli_d = 14, moduli_s = 6;
     int fastmode = 1, complex_type = GEMMUL8_COMPLEX_KARATSUBA_MULT, verbose = 0;
     double min_mnk = 134217728.0;
+    size_t max_work = 0;   // GEMMUL8_MAX_WORK_MB: cap of the cached workspace (0 = none); larger problems take the low-memory call
     Config() {
+        if (const char *e = getenv("GEMMUL8_MAX_WORK_MB")) max_work = (size_t)atoll(e) << 20;
         if (const char *e = getenv("GEMMUL8_NUM_MODULI_D")) moduli_d = (unsigned)atoi(e);
         if (const char *e = getenv("GEMMUL8_NUM_MODULI_S")) moduli_s = (unsigned)atoi(e);
         if (const char *e = getenv("GEMMUL8_FASTMODE")) fastmode = atoi(e) != 0;
@@ -94,12 +96,26 @@ bool emulate(cublasHandle_t handle, cublasOperation_t ta, cublasOperation_t tb, 
     a.compute_type = cplx ? cfg.complex_type : GEMMUL8_REAL_DEFAULT;
     a.dtype_A = a.dtype_B = a.dtype_C = dtype;
     a.stream = st;
-    const size_t need = gemmul8_b200_worksize(a.m, a.n, a.k, a.num_moduli, a.compute_type);
+    size_t need = gemmul8_b200_worksize(a.m, a.n, a.k, a.num_moduli, a.compute_type);
 
     Workspace &w = workspace();
     std::lock_guard<std::mutex> lock(w.mu);
     int dev = 0;
     cudaGetDevice(&dev);
+    // The full workspace (N (m + n) k bytes and more) may not fit beside the application's matrices, or may exceed the
+    // configured cap: real types then take the low-memory call with the largest blocks that do fit (same bits of C).
+    size_t block_rows = 0, block_cols = 0, budget = cfg.max_work;
+    if (w.device != dev || w.bytes < need) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t avail = (free_b + (w.device == dev ? w.bytes : 0)) / 10 * 9;   // what a re-allocation could get
+            if (!budget || avail < budget) budget = avail;
+        }
+    }
+    if (budget && need > budget) {
+        if (cplx || gemmul8_b200_plan_blocks(a.m, a.n, a.k, a.num_moduli, budget, &block_rows, &block_cols, &need) != GEMMUL8_OK)
+            return false;                                  // nothing fits: let cuBLAS do it
+    }
     if (w.device != dev || w.bytes < need) {
         if (w.ptr) { cudaDeviceSynchronize(); cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; }
         if (cudaMalloc(&w.ptr, need) != cudaSuccess) { cudaGetLastError(); w.ptr = nullptr; return false; }   // no room: let cuBLAS do it
@@ -109,7 +125,7 @@ bool emulate(cublasHandle_t handle, cublasOperation_t ta, cublasOperation_t tb, 
         cudaStreamWaitEvent(st, w.last, 0);   // another stream may still be using the buffer
     }
     a.work = w.ptr;
-    const int rc = gemmul8_b200_gemm(&a);
+    const int rc = block_rows ? gemmul8_b200_gemm_blocked(&a, block_rows, block_cols) : gemmul8_b200_gemm(&a);
     if (w.last) cudaEventRecord(w.last, st);
     if (rc != GEMMUL8_OK) {
         if (cfg.verbose) fprintf(stderr, "gemmul8_b200_blas: emulation refused (%s), falling back to cuBLAS\n", gemmul8_b200_last_error());
@@ -117,8 +133,8 @@ bool emulate(cublasHandle_t handle, cublasOperation_t ta, cublasOperation_t tb, 
     }
     g_intercepted.fetch_add(1);
     if (cfg.verbose)
-        fprintf(stderr, "gemmul8_b200_blas: %lld x %lld x %lld dtype %d -> %u moduli, %s mode\n", m, n, k, dtype, a.num_moduli,
-                a.fastmode ? "fast" : "accurate");
+        fprintf(stderr, "gemmul8_b200_blas: %lld x %lld x %lld dtype %d -> %u moduli, %s mode%s\n", m, n, k, dtype, a.num_moduli,
+                a.fastmode ? "fast" : "accurate", block_rows ? ", low-memory blocks" : "");
     return true;
 }
 

@@ -51,3 +51,17 @@ def test_unmodified_cublas_application_is_emulated():
     lines = [l for l in pre.stderr.splitlines() if l.startswith("gemmul8_b200_blas:")]
     assert len(lines) == 2 and "1024 x 768 x 2048" in lines[0] and "512 x 384 x 1024" in lines[1]   # the 8^3 call stayed with cuBLAS
     assert a[("T", "0")] == b[("T", "0")] == [16.0]
+
+
+@pytest.mark.gpu
+def test_interposer_takes_the_low_memory_call_when_the_workspace_is_capped():
+    """GEMMUL8_MAX_WORK_MB below workSize(): the DGEMM is emulated block by block (same bits as the plain emulation),
+    the ZGEMM -- no low-memory call for complex types -- stays with cuBLAS."""
+    build_app()
+    base = dict(os.environ, LD_PRELOAD=BLAS, GEMMUL8_VERBOSE="1", GEMMUL8_MIN_MNK=str(2 ** 24))
+    full = subprocess.run([APP], capture_output=True, text=True, env=base, check=True)
+    capped = subprocess.run([APP], capture_output=True, text=True, env=dict(base, GEMMUL8_MAX_WORK_MB="24"), check=True)
+    a, b = parse(full.stdout), parse(capped.stdout)
+    assert [v for k, v in a.items() if k[0] == "D"] == [v for k, v in b.items() if k[0] == "D"]      # bit-identical
+    lines = [l for l in capped.stderr.splitlines() if l.startswith("gemmul8_b200_blas:")]
+    assert len(lines) == 1 and "1024 x 768 x 2048" in lines[0] and "low-memory blocks" in lines[0]
