@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--sizes", default="1024,2048,4096,8192")
     ap.add_argument("--moduli", type=int, default=14)
     ap.add_argument("--accurate", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra GEMMUL8_FLAG_* bits (64 = the single-kernel GEMM + CRT)")
     ap.add_argument("--shapes", default="", help="m x n x k triples instead of squares, e.g. 16384x16384x1024,16384x16384x512 (HPL-like updates)")
     a = ap.parse_args()
     N, fast = a.moduli, not a.accurate
@@ -26,7 +27,7 @@ def main():
         B = g.phi_matrix(k, n, 0.5, torch.float64, seed=7)
         C = torch.zeros((n, m), dtype=torch.float64, device="cuda")
         work = torch.empty(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
-        args = g.make_args(0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, fast, work)
+        args = g.make_args(0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, fast, work, flags=a.flags)
         import ctypes
         call = lambda: g.lib().gemmul8_b200_gemm(ctypes.byref(args))
         for _ in range(5):
@@ -42,7 +43,7 @@ def main():
         us = e0.elapsed_time(e1) / reps * 1e3
         ph = [0.0] * 4
         for _ in range(10):
-            t = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, fast, work, flags=g.FLAG_TIMERS)
+            t = g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, fast, work, flags=g.FLAG_TIMERS | a.flags)
             ph = [x + y / 10 / 1e3 for x, y in zip(ph, t)]
         print(json.dumps({"m": m, "n": n, "k": k, "moduli": N, "fast": fast, "us_per_call_back_to_back": round(us, 1),
                           "TFLOPS": round(2.0 * m * n * k / us / 1e6, 1),
