@@ -1,0 +1,63 @@
+"""The CSVs the reference's own (unmodified) drivers wrote on B200 -- once linked against this library, once against the
+reference library (profiles/r01_reference_drivers/, produced by tools/ref_drivers.py run) -- checked offline: every
+emulation cell of the accuracy tables is the same string in both, the DGEMM table equals the reference's published GH200
+table (fixture tests/golden/published_d_accuracy_GH200.csv), and every timing row carries identical errors."""
+import glob
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIR = os.path.join(ROOT, "profiles", "r01_reference_drivers")
+
+
+def _tool():
+    spec = importlib.util.spec_from_file_location("ref_drivers", os.path.join(ROOT, "tools", "ref_drivers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _csv(lib, kind, prec):
+    c = glob.glob(os.path.join(DIR, f"{lib}_oz2_results_{prec}_{kind}_*.csv"))
+    assert len(c) == 1, c
+    return _tool().read_csv(c[0])
+
+
+def test_accuracy_tables_identical_between_libraries():
+    t = _tool()
+    for prec, cells in (("d", 760), ("f", 448)):
+        ours, moduli = t.accuracy_table(_csv("ours", "accuracy", prec))
+        ref, _ = t.accuracy_table(_csv("ref", "accuracy", prec))
+        n = 0
+        for key, row in ours.items():
+            if t.is_emulation(key[1]):
+                assert row == ref[key], key
+                n += len(row)
+        assert n == cells
+
+
+def test_dgemm_accuracy_table_equals_the_published_one():
+    t = _tool()
+    ours, moduli = t.accuracy_table(_csv("ours", "accuracy", "d"))
+    pub, pm = t.accuracy_table(t.read_csv(os.path.join(ROOT, "tests", "golden", "published_d_accuracy_GH200.csv")))
+    assert moduli == pm
+    n = 0
+    for key, row in pub.items():
+        assert ours[key] == row, key
+        n += len(row)
+    assert n == 30 * 19        # 5 phi x 3 k (<= 4096 kept in the fixture) x fast / accurate, 2..20 moduli
+
+
+def test_timing_rows_carry_identical_errors_and_are_faster():
+    t = _tool()
+    for prec, rows in (("d", 152), ("f", 112)):
+        ours, ref = t.time_table(_csv("ours", "time", prec)), t.time_table(_csv("ref", "time", prec))
+        n = 0
+        for key, o in ours.items():
+            if not t.is_emulation(key[1]):
+                continue
+            r = ref[key]
+            assert (o["relerr_max"], o["relerr_med"]) == (r["relerr_max"], r["relerr_med"]), key
+            assert float(o["TFLOPS"]) > float(r["TFLOPS"]), key
+            n += 1
+        assert n == rows
