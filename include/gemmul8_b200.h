@@ -62,6 +62,10 @@ enum {
     GEMMUL8_FLAG_STRIPS         = 1u << 10, /* gemm: column-strip pipeline on three streams (measured slower) */
     GEMMUL8_FLAG_ONLY_SCALE_A   = 1u << 11, /* real types: shifts + residues of A only, then return (B may still be in flight) */
     GEMMUL8_FLAG_SKIP_SCALE_A   = 1u << 12, /* real types: A's shifts + residues are already in `work` (previous flag)        */
+    GEMMUL8_FLAG_ONLY_BOUND     = 1u << 14, /* real types, accurate mode: bound product only; its int32 row maxima (m) are left at
+                                               work + off_A8i + sizeA, its column maxima (n) at work + off_B8i + sizeB           */
+    GEMMUL8_FLAG_SKIP_BOUND     = 1u << 15, /* real types, accurate mode: the maxima are already there (previous flag, possibly
+                                               combined with those of other blocks by the caller)                               */
     GEMMUL8_FLAG_PHASE_LOG      = 1u << 13  /* record the phase boundaries as events WITHOUT synchronising; the times of all such
                                                calls of this host thread are summed by gemmul8_b200_phase_log_collect()      */
 };

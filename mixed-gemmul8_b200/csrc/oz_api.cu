@@ -305,18 +305,25 @@ int gemm_real(gemmul8_b200_args *a) {
     } else {
         if (a->flags & GEMMUL8_FLAG_ONLY_SCALE_A) return GEMMUL8_OK;   // accurate mode needs both operands: all work in the second call
         // reference: int8tc::scaling, GEMMul8/src/scaling.hpp:3053-3136
-        OZ_CUDA(oz::launch_bound_extract(a->dtype_A, a_strided, a->A, a->lda, m, k, A8i, L.lda8i, sftA, st), "bound extract A");
-        OZ_CUDA(oz::launch_bound_extract(a->dtype_B, b_strided, a->B, a->ldb, n, k, B8i, L.lda8i, sftB, st), "bound extract B");
         // The bound product only needs its row / column maxima.  They live in the (still unused)
         // second modulus slice of A8i / B8i: 4*m_pad <= lda8i*m_pad and 4*n <= lda8i*n always hold.
         int32_t *rowmax = reinterpret_cast<int32_t *>(A8i + L.sizeA);
         int32_t *colmax = reinterpret_cast<int32_t *>(B8i + L.sizeB);
-        OZ_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(int32_t) * m, st), "memset row maxima");
-        OZ_CUDA(cudaMemsetAsync(colmax, 0, sizeof(int32_t) * n, st), "memset col maxima");
-        oz::GemmProblem bp{};
-        bp.A8i = A8i; bp.B8i = B8i; bp.rowsA = m; bp.rowsB = n; bp.ld8i = L.lda8i; bp.sizeA = L.sizeA; bp.sizeB = L.sizeB;
-        bp.num_slices = 1; bp.first_modulus = 0; bp.rowmax = rowmax; bp.colmax = colmax;
-        OZ_CUDA(gemm(bp, oz::EPI_ABSMAX, st), "bound product");
+        // A caller that holds one block of a partitioned C (distributed.py) splits the call here: ..._ONLY_BOUND leaves the
+        // maxima of ITS block's bound product in `work`, the caller takes the maximum over the blocks that share the rows /
+        // the columns (one tiny all-reduce each), and ..._SKIP_BOUND continues with those: the shifts, and with them every
+        // bit of C, are then the ones of the unpartitioned call.
+        if (!(a->flags & GEMMUL8_FLAG_SKIP_BOUND)) {
+            OZ_CUDA(oz::launch_bound_extract(a->dtype_A, a_strided, a->A, a->lda, m, k, A8i, L.lda8i, sftA, st), "bound extract A");
+            OZ_CUDA(oz::launch_bound_extract(a->dtype_B, b_strided, a->B, a->ldb, n, k, B8i, L.lda8i, sftB, st), "bound extract B");
+            OZ_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(int32_t) * m, st), "memset row maxima");
+            OZ_CUDA(cudaMemsetAsync(colmax, 0, sizeof(int32_t) * n, st), "memset col maxima");
+            oz::GemmProblem bp{};
+            bp.A8i = A8i; bp.B8i = B8i; bp.rowsA = m; bp.rowsB = n; bp.ld8i = L.lda8i; bp.sizeA = L.sizeA; bp.sizeB = L.sizeB;
+            bp.num_slices = 1; bp.first_modulus = 0; bp.rowmax = rowmax; bp.colmax = colmax;
+            OZ_CUDA(gemm(bp, oz::EPI_ABSMAX, st), "bound product");
+        }
+        if (a->flags & GEMMUL8_FLAG_ONLY_BOUND) { timer.mark(); timer.finish(a->timers_ns); return GEMMUL8_OK; }
         const float l2 = oz::host_tab::OZ_LOG2M_ACC[ti];
         OZ_CUDA(oz::launch_accurate_shifts(m, rowmax, l2, sftA, st), "accurate shifts A");
         OZ_CUDA(oz::launch_accurate_shifts(n, colmax, l2, sftB, st), "accurate shifts B");

@@ -91,6 +91,22 @@ def pgemm(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, c_block, num_moduli
     if not overlap:
         a_panel = grid.gather_a_panel(a_slice, m_loc, k)
         b_panel = grid.gather_b_panel(b_slice, n_loc, k)
+        if not fastmode and not a_slice.is_complex() and a_slice.is_cuda and grid.world > 1 and k > 0:
+            # Accurate mode: the shift of a row of A comes from the maximum of its bound-product row over ALL n columns,
+            # i.e. over the Q blocks of this grid row (and the shift of a column of B over the P blocks of its grid
+            # column).  Bound product of the own block, one int32 max-all-reduce per direction, then the rest of the
+            # call: same shifts, same bits of C as the unpartitioned product.
+            pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
+                     num_moduli, False, work, flags=pkg.FLAG_ONLY_BOUND)
+            L = pkg.work_layout(m_loc, n_loc, k, num_moduli)
+            rowmax = work[L.off_A8i + L.sizeA:L.off_A8i + L.sizeA + 4 * m_loc].view(torch.int32)
+            colmax = work[L.off_B8i + L.sizeB:L.off_B8i + L.sizeB + 4 * n_loc].view(torch.int32)
+            if grid.Q > 1:
+                dist.all_reduce(rowmax, op=dist.ReduceOp.MAX, group=grid.row_group)
+            if grid.P > 1:
+                dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=grid.col_group)
+            return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
+                            num_moduli, False, work, flags=flags | pkg.FLAG_SKIP_BOUND)
         return pkg.gemm(None, 0, 0, m_loc, n_loc, k, alpha, a_panel, m_loc, b_panel, k, beta, c_block, m_loc,
                         num_moduli, fastmode, work, flags=flags)
     # The row and the column communicator are different NCCL communicators with their own streams, so the

@@ -432,6 +432,32 @@ def test_empty_inner_dimension(g, dt):
     assert torch.equal(torch.view_as_real(C) if t.is_complex else C, torch.view_as_real(C0) if t.is_complex else C0)
 
 
+def test_accurate_mode_bound_can_be_split_from_the_call(g):
+    """FLAG_ONLY_BOUND then FLAG_SKIP_BOUND (what a partitioned caller does around its max-all-reduce) == one call;
+    and maxima raised by the caller (as if another block had larger bound products) change the shifts accordingly."""
+    torch = torch_()
+    m, n, k, N = 700, 500, 900, 14
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=21)
+    want, v = run_ours(g, m, n, k, N, False, A, B)
+    work = torch.zeros(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+    C = torch.zeros_like(want)
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, False, work, flags=g.FLAG_ONLY_BOUND)
+    L = g.work_layout(m, n, k, N)
+    rowmax = work[L.off_A8i + L.sizeA:L.off_A8i + L.sizeA + 4 * m].view(torch.int32)
+    assert int(rowmax.min()) > 0 and bool((C == 0).all())
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, False, work, flags=g.FLAG_SKIP_BOUND)
+    torch.cuda.synchronize()
+    w = g.work_views(work, L, N, m, n)
+    assert torch.equal(C, want) and torch.equal(w["sftA"], v["sftA"]) and torch.equal(w["sftB"], v["sftB"])
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, False, work, flags=g.FLAG_ONLY_BOUND)
+    rowmax.mul_(16)                                              # a 16x larger bound: 0.51 * 4 = 2.04 -> 2 or 3 bits less
+    g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, False, work, flags=g.FLAG_SKIP_BOUND)
+    torch.cuda.synchronize()
+    d = (g.work_views(work, L, N, m, n)["sftA"].int() - v["sftA"].int())     # stored negated: smaller shift = larger stored value
+    assert int(d.min()) >= 2 and int(d.max()) <= 3
+    assert float((C - want).abs().max()) <= 1e-7 * float(want.abs().max())      # still the same product, a few bits coarser
+
+
 def test_phase_log_records_without_synchronising(g):
     """FLAG_PHASE_LOG: phase boundaries go to a per-thread event log (no host wait); collect() sums them later."""
     torch = torch_()

@@ -44,6 +44,30 @@ def main():
         good = same and err < (1e-6 if N >= 14 else 1e-3)      # 9 moduli carry ~1e-5 by construction
         print(f"rank {rank} grid {grid.P}x{grid.Q} block ({grid.p},{grid.q}) m={m} n={n} k={k} N={N}: identical={same} relerr_max={err:.3e}", flush=True)
         ok = ok and good
+        # accurate mode: the partitioned call (bound maxima combined over the grid row / column) against the
+        # UNPARTITIONED accurate product of the full matrices, computed here on every rank: its block, bit for bit
+        C3 = torch.zeros_like(C1)
+        dmod.pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, C3, N, False, work)
+        if grid.P > 1:
+            parts = [torch.empty_like(a_panel) for _ in range(grid.P)]
+            dist.all_gather(parts, a_panel.contiguous(), group=grid.col_group)
+            A_full = torch.cat(parts, dim=1).contiguous()              # (k, m): column-major m x k
+        else:
+            A_full = a_panel
+        if grid.Q > 1:
+            parts = [torch.empty_like(b_panel) for _ in range(grid.Q)]
+            dist.all_gather(parts, b_panel.contiguous(), group=grid.row_group)
+            B_full = torch.cat(parts, dim=0).contiguous()              # (n, k): column-major k x n
+        else:
+            B_full = b_panel
+        Cf = torch.zeros((n, m), dtype=torch.float64, device="cuda")
+        wf = torch.empty(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+        g.gemm(None, 0, 0, m, n, k, 1.0, A_full, m, B_full, k, 0.0, Cf, m, N, False, wf)
+        torch.cuda.synchronize()
+        blk = Cf[grid.q * n_loc:(grid.q + 1) * n_loc, grid.p * m_loc:(grid.p + 1) * m_loc]
+        acc_same = torch.equal(C3, blk) and bool(C3.abs().sum() > 0)
+        print(f"rank {rank} accurate mode, block of the unpartitioned product: identical={acc_same}", flush=True)
+        ok = ok and acc_same
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     if rank == 0:
