@@ -142,7 +142,12 @@ struct PhaseTimer {
             PhaseLog::Entry e;
             for (int i = 0; i < 5; ++i) e.ev[i] = ev[i];
             e.n = n;
-            g_phase_log.entries.push_back(e);
+            auto &log_entries = g_phase_log.entries;
+            if (log_entries.size() >= 4096) {          // never collected: keep the most recent calls only
+                for (auto &old_ev : log_entries.front().ev) g_phase_log.pool.push_back(old_ev);
+                log_entries.erase(log_entries.begin());
+            }
+            log_entries.push_back(e);
             return;
         }
         cudaEventSynchronize(ev[n - 1]);
