@@ -66,6 +66,9 @@ enum {
                                                work + off_A8i + sizeA, its column maxima (n) at work + off_B8i + sizeB           */
     GEMMUL8_FLAG_SKIP_BOUND     = 1u << 15, /* real types, accurate mode: the maxima are already there (previous flag, possibly
                                                combined with those of other blocks by the caller)                               */
+    GEMMUL8_FLAG_DEVICE_SCALARS = 1u << 16, /* alpha and beta point to DEVICE memory (CUBLAS_POINTER_MODE_DEVICE callers): they are read by
+                                               the CRT kernel, never on the host (the reference dereferences on the host,
+                                               GEMMul8/src/gemmul8.cu:288).  Not for gemm_host.                                  */
     GEMMUL8_FLAG_PHASE_LOG      = 1u << 13  /* record the phase boundaries as events WITHOUT synchronising; the times of all such
                                                calls of this host thread are summed by gemmul8_b200_phase_log_collect()      */
 };
@@ -74,10 +77,10 @@ enum {
 typedef struct {
     int op_A, op_B;            /* gemmul8_op_t */
     size_t m, n, k;
-    const void *alpha;         /* host pointer, type of C */
+    const void *alpha;         /* host pointer, type of C (device pointer with GEMMUL8_FLAG_DEVICE_SCALARS) */
     const void *A; size_t lda; /* device */
     const void *B; size_t ldb; /* device */
-    const void *beta;          /* host pointer, type of C */
+    const void *beta;          /* host pointer, type of C (device pointer with GEMMUL8_FLAG_DEVICE_SCALARS) */
     void *C; size_t ldc;       /* device */
     unsigned num_moduli;       /* 2..20 */
     int fastmode;              /* 1 = fast (vector-norm bound), 0 = accurate (int8 bound product) */
@@ -108,6 +111,20 @@ typedef struct {
     size_t total;                   /* == gemmul8_b200_worksize()                     */
 } gemmul8_b200_layout;
 
+/* Optional, once per device (device < 0: the current one): everything the first gemm call would otherwise do lazily --
+ * read the tuning defaults from the environment and probe the SM placement table of the CTA-pair GEMM (one small
+ * allocation kept for the life of the process, one launch on a private stream).  A first gemm call that is being
+ * captured into a CUDA graph never probes; it runs without the table (same results, work assigned by block index).
+ * The reference has no such call (it re-uploads its constant tables on every gemm, gemmul8.cu:236-241). */
+int gemmul8_b200_init(int device);
+
+/* Tuning / debug options, process-wide and thread-safe.  Their defaults come from the environment, read once:
+ *   "gemm_pair"  (OZ_GEMM_PAIR)  -1 auto | 0 single-CTA kernel | 1 CTA-pair kernel      "band" (OZ_BAND), "pair_band" (OZ_PAIR_BAND)
+ *   "pair_stages" (OZ_PAIR_STAGES) 0 auto | 4 | 5 | 6     "encode_reference" (GEMMUL8_B200_ENCODE=reference) 0 | 1
+ *   "fused_k" (GEMMUL8_B200_FUSED_K) largest k that takes the single-kernel product + CRT path (0 = never) */
+int gemmul8_b200_set_option(const char *name, int value);
+int gemmul8_b200_get_option(const char *name, int *value);
+
 /* reference: gemmul8::workSize, GEMMul8/src/gemmul8.cu:129-147.  Returns 0 (and prints
  * "Unknown compute type") for an invalid compute_type, as the reference does. */
 size_t gemmul8_b200_worksize(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type);
@@ -137,7 +154,7 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *args, int parts, size_t row0, size
  * op(B) resident -- N (m + n) k bytes, 184 GiB at 65536^3 (GEMMul8/src/gemmul8.cu:27-60); the reference's
  * README.md:3 points at a `memory-lt` branch for this, which is not in the tree.  Here C is produced in blocks of
  * block_rows x block_cols (multiples of 256, or the whole dimension) and `args->work` only needs
- * gemmul8_b200_worksize_blocked() bytes: N k (block_rows + block_cols) + N block_rows block_cols + 6 (m + n)
+ * gemmul8_b200_worksize_blocked() bytes: N k (block_rows + block_cols) + N block_rows block_cols + 6 (m + n) + 1024
  * (+ padding).  Result bits are those of gemmul8_b200_gemm (shifts are per row / column, residues and CRT per
  * element, the accurate-mode bound is a maximum over blocks).  gemmul8_b200_plan_blocks picks the block sizes with
  * the least re-encoding for a workspace of at most `max_bytes`.  timers_ns (GEMMUL8_FLAG_TIMERS) are the sums of the

@@ -24,12 +24,14 @@ F32, F64, C32, C64 = 0, 1, 2, 3
 FLAG_TIMERS, FLAG_STAGE_SCALING, FLAG_STAGE_RESIDUES, FLAG_FUSED_CRT, FLAG_GEMM_SIMT, FLAG_HOST_SERIAL, FLAG_STRIPS = 1, 1 << 4, 1 << 5, 1 << 6, 1 << 8, 1 << 9, 1 << 10
 FLAG_ONLY_SCALE_A, FLAG_SKIP_SCALE_A, FLAG_PHASE_LOG = 1 << 11, 1 << 12, 1 << 13
 FLAG_ONLY_BOUND, FLAG_SKIP_BOUND = 1 << 14, 1 << 15
+FLAG_DEVICE_SCALARS = 1 << 16
 
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",
     "gemmul8_b200_gemm_host", "gemmul8_b200_gemm_part",
     "gemmul8_b200_worksize_blocked", "gemmul8_b200_plan_blocks", "gemmul8_b200_gemm_blocked", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
     "gemmul8_b200_phase_log_collect", "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
+    "gemmul8_b200_init", "gemmul8_b200_set_option", "gemmul8_b200_get_option",
 )
 
 
@@ -101,6 +103,12 @@ def lib():
         L.gemmul8_b200_phase_log_collect.restype = C.c_int
         L.gemmul8_b200_phase_log_collect.argtypes = [C.POINTER(C.c_double * 4), C.POINTER(C.c_uint)]
         L.gemmul8_b200_launch_count.restype = C.c_ulonglong
+        L.gemmul8_b200_init.restype = C.c_int
+        L.gemmul8_b200_init.argtypes = [C.c_int]
+        L.gemmul8_b200_set_option.restype = C.c_int
+        L.gemmul8_b200_set_option.argtypes = [C.c_char_p, C.c_int]
+        L.gemmul8_b200_get_option.restype = C.c_int
+        L.gemmul8_b200_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
         L.gemmul8_b200_last_error.restype = C.c_char_p
         L.gemmul8_b200_version.restype = C.c_char_p
         _lib = L
@@ -126,6 +134,22 @@ def aux():
 def _check(rc):
     if rc != 0:
         raise Gemmul8Error(f"gemmul8_b200 status {rc}: {lib().gemmul8_b200_last_error().decode()}")
+
+
+def init(device=-1):
+    """gemmul8_b200_init: read the tuning defaults and probe the SM placement table of `device` (default: current)."""
+    _check(lib().gemmul8_b200_init(device))
+
+
+def set_option(name, value):
+    """Process-wide tuning / debug option (see include/gemmul8_b200.h)."""
+    _check(lib().gemmul8_b200_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = C.c_int()
+    _check(lib().gemmul8_b200_get_option(name.encode(), C.byref(v)))
+    return v.value
 
 
 def workSize(m, n, k, num_moduli, computeType=REAL_DEFAULT):
@@ -160,9 +184,13 @@ def make_args(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_m
     a = Args()
     a.op_A, a.op_B, a.m, a.n, a.k = op_A, op_B, m, n, k
     a.dtype_A, a.dtype_B, a.dtype_C = _dtype_tag(A), _dtype_tag(B), _dtype_tag(Cmat)
-    a._alpha = _scalar_buf(alpha, a.dtype_C)
-    a._beta = _scalar_buf(beta, a.dtype_C)
-    a.alpha, a.beta = C.addressof(a._alpha), C.addressof(a._beta)
+    if flags & FLAG_DEVICE_SCALARS:      # alpha, beta: one-element CUDA tensors of C's dtype, read on the device
+        a._alpha, a._beta = alpha, beta
+        a.alpha, a.beta = alpha.data_ptr(), beta.data_ptr()
+    else:
+        a._alpha = _scalar_buf(alpha, a.dtype_C)
+        a._beta = _scalar_buf(beta, a.dtype_C)
+        a.alpha, a.beta = C.addressof(a._alpha), C.addressof(a._beta)
     a.A, a.lda, a.B, a.ldb, a.C, a.ldc = A.data_ptr(), lda, B.data_ptr(), ldb, Cmat.data_ptr(), ldc
     a.num_moduli, a.fastmode, a.work, a.compute_type = num_moduli, int(bool(fastmode)), work.data_ptr(), computeType
     if stream is None and Cmat.is_cuda:

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -23,9 +24,48 @@
 namespace oz {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-bool encode_reference_chain() {
-    const char *e = getenv("GEMMUL8_B200_ENCODE");
-    return e && !strcmp(e, "reference");
+
+// Options: atomics behind a snapshot struct; the environment is consulted exactly once.
+namespace {
+struct Option { const char *name; const char *env; std::atomic<int> value; int lo, hi; };
+Option g_options[] = {
+    {"gemm_pair", "OZ_GEMM_PAIR", {-1}, -1, 1},
+    {"band", "OZ_BAND", {16}, 1, 1024},
+    {"pair_band", "OZ_PAIR_BAND", {8}, 1, 1024},
+    {"pair_stages", "OZ_PAIR_STAGES", {0}, 0, 6},
+    {"encode_reference", nullptr, {0}, 0, 1},
+    {"fused_k", "GEMMUL8_B200_FUSED_K", {0}, 0, 1 << 17},
+};
+std::once_flag g_options_once;
+void load_options_from_env() {
+    std::call_once(g_options_once, [] {
+        for (auto &o : g_options) {
+            const char *e = o.env ? getenv(o.env) : nullptr;
+            if (e && *e) {
+                const int v = atoi(e);
+                if (v >= o.lo && v <= o.hi) o.value.store(v, std::memory_order_relaxed);
+            }
+        }
+        const char *e = getenv("GEMMUL8_B200_ENCODE");
+        if (e && !strcmp(e, "reference")) g_options[4].value.store(1, std::memory_order_relaxed);
+    });
+}
+Option *find_option(const char *name) {
+    if (!name) return nullptr;
+    for (auto &o : g_options) if (!strcmp(o.name, name)) return &o;
+    return nullptr;
+}
+}  // namespace
+const Tuning &tuning() {
+    load_options_from_env();
+    thread_local Tuning t;
+    t.gemm_pair        = g_options[0].value.load(std::memory_order_relaxed);
+    t.band             = g_options[1].value.load(std::memory_order_relaxed);
+    t.pair_band        = g_options[2].value.load(std::memory_order_relaxed);
+    t.pair_stages      = g_options[3].value.load(std::memory_order_relaxed);
+    t.encode_reference = g_options[4].value.load(std::memory_order_relaxed);
+    t.fused_k          = g_options[5].value.load(std::memory_order_relaxed);
+    return t;
 }
 }  // namespace oz
 
@@ -43,6 +83,13 @@ int fail_cuda(cudaError_t e, const char *where) {
 
 inline size_t ceil_to(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Per-launch scratch of the pair GEMM (see GemmProblem::claims): the start of the int32 area that the reference carves for
+// its per-modulus product and that this library never fills.  Launches that share a `work` buffer are ordered on one
+// stream by every caller in this file; calls that may overlap have their own `work`.
+uint32_t *claims_of(uint8_t *work, const oz::Layout &L) {
+    return 4 * L.sizeC >= oz::kClaimBytes ? reinterpret_cast<uint32_t *>(work + L.off_C32i) : nullptr;
+}
+bool dev_scalars(const gemmul8_b200_args *a) { return (a->flags & GEMMUL8_FLAG_DEVICE_SCALARS) != 0; }
 bool is_complex(int dt) { return dt == GEMMUL8_C32 || dt == GEMMUL8_C64; }
 size_t elem_size(int dt) { return dt == GEMMUL8_F32 ? 4 : dt == GEMMUL8_F64 ? 8 : dt == GEMMUL8_C32 ? 8 : 16; }
 
@@ -72,7 +119,7 @@ bool compute_layout(size_t m, size_t n, size_t k, unsigned N, int ct, oz::Layout
     return true;
 }
 
-int check_args(const gemmul8_b200_args *a) {
+int check_args(const gemmul8_b200_args *a, bool need_work = true) {
     if (!a) return fail(GEMMUL8_ERR_ARGUMENT, "null argument block");
     if (a->num_moduli < 2 || a->num_moduli > 20) return fail(GEMMUL8_ERR_ARGUMENT, "num_moduli must be in 2..20");
     if (a->k > (size_t(1) << 17)) return fail(GEMMUL8_ERR_ARGUMENT, "k must be <= 2^17");
@@ -89,7 +136,7 @@ int check_args(const gemmul8_b200_args *a) {
         fprintf(stderr, "Unsupported compute type for the argument types.\n");
         return fail(GEMMUL8_ERR_COMPUTETYPE, "unsupported compute type for the argument types");
     }
-    if (a->m && a->n && (!a->C || !a->work || !a->alpha || !a->beta)) return fail(GEMMUL8_ERR_ARGUMENT, "null pointer");
+    if (a->m && a->n && (!a->C || (need_work && !a->work) || !a->alpha || !a->beta)) return fail(GEMMUL8_ERR_ARGUMENT, "null pointer");
     if (a->m && a->n && a->k && (!a->A || !a->B)) return fail(GEMMUL8_ERR_ARGUMENT, "null matrix pointer");
     return GEMMUL8_OK;
 }
@@ -101,7 +148,9 @@ int check_args(const gemmul8_b200_args *a) {
 //                           timed region, with no host wait between or after the calls)
 struct PhaseLog {
     struct Entry { cudaEvent_t ev[5]; int n; };
-    std::vector<Entry> entries;
+    static constexpr size_t kCapacity = 4096;   // never collected: the most recent calls are kept (ring)
+    std::vector<Entry> ring;                     // at most kCapacity entries; `head` is the oldest once it is full
+    size_t head = 0;
     std::vector<cudaEvent_t> pool;   // recycled events of device `dev` (an event belongs to the device it was created on)
     int dev = -1;
     cudaEvent_t get() {
@@ -117,42 +166,48 @@ struct PhaseLog {
         cudaEventCreate(&e);
         return e;
     }
+    void put(cudaEvent_t e) { if (e) pool.push_back(e); }
+    void push(const Entry &e) {
+        if (ring.size() < kCapacity) { ring.push_back(e); return; }
+        for (auto old_ev : ring[head].ev) put(old_ev);
+        ring[head] = e;
+        head = (head + 1) % kCapacity;
+    }
 };
 thread_local PhaseLog g_phase_log;
 
 struct PhaseTimer {
-    bool on, log; cudaStream_t st; cudaEvent_t ev[5]; int n = 0;
+    bool on, log; cudaStream_t st; cudaEvent_t ev[5] = {}; int n = 0; bool handed_over = false;
     PhaseTimer(unsigned flags, cudaStream_t s)
         : on((flags & (GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_PHASE_LOG)) != 0), log((flags & GEMMUL8_FLAG_PHASE_LOG) != 0), st(s) {
         if (on) for (auto &e : ev) e = g_phase_log.get();
     }
-    void mark() { if (on) cudaEventRecord(ev[n++], st); }
+    PhaseTimer(const PhaseTimer &) = delete;
+    PhaseTimer &operator=(const PhaseTimer &) = delete;
+    ~PhaseTimer() {   // every exit path, error returns included: the events go back to the pool unless the log took them
+        if (on && !handed_over) for (auto e : ev) g_phase_log.put(e);
+    }
+    void mark() { if (on && n < 5) cudaEventRecord(ev[n++], st); }
     // marks: 0 start, 1 after scaling, 2 after gemm(+residues), 3 after crt
-    static void spans(cudaEvent_t *ev, int n, double *out_ns) {
+    static void spans(const cudaEvent_t *ev, int n, double *out_ns) {
         float ms;
         const int slot[3] = {0, 1, 3};
         for (int i = 0; i + 1 < n && i < 3; ++i) {
-            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-            out_ns[slot[i]] += (double)ms * 1e6;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) out_ns[slot[i]] += (double)ms * 1e6;
         }
     }
     void finish(double *out_ns) {
-        if (!on) return;
+        if (!on || n == 0) return;
         if (log) {
             PhaseLog::Entry e;
             for (int i = 0; i < 5; ++i) e.ev[i] = ev[i];
             e.n = n;
-            auto &log_entries = g_phase_log.entries;
-            if (log_entries.size() >= 4096) {          // never collected: keep the most recent calls only
-                for (auto &old_ev : log_entries.front().ev) g_phase_log.pool.push_back(old_ev);
-                log_entries.erase(log_entries.begin());
-            }
-            log_entries.push_back(e);
+            g_phase_log.push(e);
+            handed_over = true;
             return;
         }
         cudaEventSynchronize(ev[n - 1]);
         spans(ev, n, out_ns);
-        for (auto &e : ev) g_phase_log.pool.push_back(e);
     }
 };
 
@@ -245,7 +300,7 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
 
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.rowsA = m; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
-    gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
     gp.share_sm = true;   // encoder / CRT blocks of the side streams must fit beside the persistent GEMM CTAs
     for (int j = 0; j < strips; ++j) {
         const size_t c0 = cb[j], c1 = cb[j + 1];
@@ -256,7 +311,7 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
         OZ_CUDA(cudaEventRecord(S.evG[j], st), "event record");
         OZ_CUDA(cudaStreamWaitEvent(S.sC, S.evG[j], 0), "stream wait");
         OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, c1 - c0, gp.C8u, L.m_pad, L.sizeC, static_cast<uint8_t *>(a->C) + c0 * a->ldc * esC,
-                               a->ldc, sftA, sftB + c0, a->alpha, a->beta, S.sC), "crt");
+                               a->ldc, sftA, sftB + c0, a->alpha, a->beta, dev_scalars(a), S.sC), "crt");
     }
     OZ_CUDA(cudaEventRecord(S.done, S.sC), "event record");
     OZ_CUDA(cudaStreamWaitEvent(st, S.done, 0), "stream wait");
@@ -344,7 +399,7 @@ int gemm_real(gemmul8_b200_args *a) {
     const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;  // numM == 2 (N >= 8) and fp64 out
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.B8i = B8i; gp.rowsA = m; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
-    gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
     // Default: item-major GEMM + the stand-alone CRT kernel.  The single-kernel variant (every CTA walks all
     // moduli of its tile, CRT warps behind the last modulus) is kept behind GEMMUL8_FLAG_FUSED_CRT: on
     // B200 its tile-major schedule costs more L2 misses than the CRT pass saves ("What was tried").
@@ -363,7 +418,7 @@ int gemm_real(gemmul8_b200_args *a) {
     if (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
 
     // ---------------- phase 3: CRT + inverse scaling ----------------
-    OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, n, C8u, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, st), "crt");
+    OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, n, C8u, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, dev_scalars(a), st), "crt");
     timer.mark();
     timer.finish(a->timers_ns);
     return GEMMUL8_OK;
@@ -442,7 +497,7 @@ int gemm_complex(gemmul8_b200_args *a) {
     // ---------------- phases 1+2: products mod m_j ----------------
     oz::GemmProblem gp{};
     gp.rowsA = rowsA; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
-    gp.num_slices = N; gp.first_modulus = 0; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    gp.num_slices = N; gp.first_modulus = 0; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
     auto product = [&](const int8_t *A8, const int8_t *B8, uint8_t *C8, int combine, uint8_t *aux) -> cudaError_t {
         gp.A8i = A8; gp.B8i = B8; gp.C8u = C8; gp.combine = combine; gp.C8u_aux = aux;
         return gemm(gp, oz::EPI_RESIDUE, st);
@@ -466,7 +521,7 @@ int gemm_complex(gemmul8_b200_args *a) {
 
     // ---------------- phase 3: CRT + inverse scaling ----------------
     const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_C64;
-    OZ_CUDA(oz::launch_crt_complex(a->dtype_C, split, N, m, n, C_re, C_im, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, st), "crt");
+    OZ_CUDA(oz::launch_crt_complex(a->dtype_C, split, N, m, n, C_re, C_im, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, dev_scalars(a), st), "crt");
     timer.mark();
     timer.finish(a->timers_ns);
     return GEMMUL8_OK;
@@ -503,7 +558,7 @@ int gemmul8_b200_gemm(gemmul8_b200_args *a) {
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
         return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
     if (a->k == 0) {   // empty product: C = beta * C (the reference launches its kernels on empty operands: undefined)
-        OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, static_cast<cudaStream_t>(a->stream)), "scale C");
+        OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, dev_scalars(a), static_cast<cudaStream_t>(a->stream)), "scale C");
         return GEMMUL8_OK;
     }
     if (is_complex(a->dtype_C)) {
@@ -566,12 +621,12 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
     }
     if ((parts & GEMMUL8_PART_PRODUCT) && row1 > row0 && col1 > col0 && k == 0) {
         OZ_CUDA(oz::launch_scale_c(a->dtype_C, row1 - row0, col1 - col0, static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, a->ldc,
-                                   a->beta, st), "scale C");
+                                   a->beta, dev_scalars(a), st), "scale C");
     } else if ((parts & GEMMUL8_PART_PRODUCT) && row1 > row0 && col1 > col0) {
         const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;
         oz::GemmProblem gp{};
         gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
-        gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+        gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
         gp.A8i = A8i + row0 * L.lda8i; gp.rowsA = row1 - row0;
         gp.B8i = B8i + col0 * L.lda8i; gp.rowsB = col1 - col0;
         gp.C8u = C8u + col0 * L.m_pad + row0;
@@ -581,7 +636,7 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
         timer.mark();
         OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, row1 - row0, col1 - col0, gp.C8u, L.m_pad, L.sizeC,
                                static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, a->ldc, sftA + row0, sftB + col0, a->alpha, a->beta,
-                               st), "crt");
+                               dev_scalars(a), st), "crt");
     }
     timer.mark();
     timer.finish(a->timers_ns);
@@ -606,7 +661,7 @@ struct BlockPlan {
     size_t mb, nb;          // block_rows, block_cols (multiples of 256, or the whole dimension)
     bool outer_rows;        // true: for row blocks { for column blocks }, else the other way round
     size_t lda8i, mb_pad, sizeA, sizeB, sizeC;
-    size_t off_A8i, off_B8i, off_C8u, off_sftA, off_sftB, off_rowmax, off_colmax, total;
+    size_t off_A8i, off_B8i, off_C8u, off_sftA, off_sftB, off_rowmax, off_colmax, off_claims, total;
 };
 
 bool carve_blocks(size_t m, size_t n, size_t k, unsigned N, size_t mb, size_t nb, BlockPlan &P) {
@@ -626,6 +681,7 @@ bool carve_blocks(size_t m, size_t n, size_t k, unsigned N, size_t mb, size_t nb
     P.off_sftB = off;   off += 2 * ceil_to(n, 16);
     P.off_rowmax = off; off += 4 * ceil_to(m, 16);
     P.off_colmax = off; off += 4 * ceil_to(n, 16);
+    P.off_claims = off; off += oz::kClaimBytes;
     P.total = off;
     const size_t Rb = (m + P.mb - 1) / P.mb, Cb = (n + P.nb - 1) / P.nb;
     // elements encoded more than once: inner operand, once per outer block (unless it is a single block)
@@ -737,6 +793,7 @@ int gemm_blocked_real(gemmul8_b200_args *a, const BlockPlan &P) {
     oz::GemmProblem gp{};
     gp.ld8i = P.lda8i; gp.sizeA = P.sizeA; gp.sizeB = P.sizeB; gp.num_slices = N; gp.first_modulus = 0;
     gp.ldc8u = P.mb_pad; gp.sizeC = P.sizeC; gp.A8i = A8i; gp.B8i = B8i; gp.C8u = C8u;
+    gp.claims = reinterpret_cast<uint32_t *>(work + P.off_claims);
     for (size_t o = 0; o < (P.outer_rows ? Rb : Cb); ++o) {
         for (size_t q = 0; q < (P.outer_rows ? Cb : Rb); ++q) {
             const size_t i = P.outer_rows ? o : q, j = P.outer_rows ? q : o;
@@ -761,7 +818,7 @@ int gemm_blocked_real(gemmul8_b200_args *a, const BlockPlan &P) {
             OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
             timer.mark(1);
             OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, r1 - r0, c1 - c0, C8u, P.mb_pad, P.sizeC,
-                                   static_cast<uint8_t *>(a->C) + (c0 * a->ldc + r0) * esC, a->ldc, sftA + r0, sftB + c0, a->alpha, a->beta, st),
+                                   static_cast<uint8_t *>(a->C) + (c0 * a->ldc + r0) * esC, a->ldc, sftA + r0, sftB + c0, a->alpha, a->beta, dev_scalars(a), st),
                     "crt");
             timer.mark(3);
         }
@@ -805,7 +862,7 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
         return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
     if (a->k == 0) {
-        OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, static_cast<cudaStream_t>(a->stream)), "scale C");
+        OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, dev_scalars(a), static_cast<cudaStream_t>(a->stream)), "scale C");
         return GEMMUL8_OK;
     }
     return gemm_blocked_real(a, P);
@@ -895,7 +952,7 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
 
     oz::GemmProblem gp{};
     gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
-    gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC;
+    gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
     auto strip = [&](size_t r0, size_t r1, size_t c0, size_t c1, cudaEvent_t done) -> int {
         if (r1 <= r0 || c1 <= c0) return GEMMUL8_OK;
         gp.A8i = A8i + r0 * L.lda8i; gp.rowsA = r1 - r0;
@@ -903,7 +960,7 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
         gp.C8u = C8u + c0 * L.m_pad + r0;
         OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
         OZ_CUDA(oz::launch_crt(h->dtype_C, split, N, r1 - r0, c1 - c0, gp.C8u, L.m_pad, L.sizeC, dC + (c0 * h->ldc + r0) * esC, h->ldc,
-                               sftA + r0, sftB + c0, h->alpha, h->beta, st), "crt");
+                               sftA + r0, sftB + c0, h->alpha, h->beta, false, st), "crt");
         OZ_CUDA(cudaEventRecord(done, st), "event record");
         OZ_CUDA(cudaStreamWaitEvent(r.out, done, 0), "stream wait");
         // rows [r0, r1) of columns [c0, c1) of C
@@ -950,8 +1007,9 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
 extern "C" {
 
 int gemmul8_b200_gemm_host(gemmul8_b200_args *h, void *dev_scratch) {
-    int rc = check_args(h);
+    int rc = check_args(h, /*need_work=*/false);   // the workspace is carved out of dev_scratch; args->work is not read
     if (rc) return rc;
+    if (dev_scalars(h)) return fail(GEMMUL8_ERR_ARGUMENT, "gemm_host: alpha / beta are host scalars here");
     if (h) for (double &t : h->timers_ns) t = 0.0;
     if (!dev_scratch) return fail(GEMMUL8_ERR_ARGUMENT, "null scratch");
     if (h->m == 0 || h->n == 0) return GEMMUL8_OK;
@@ -1005,15 +1063,46 @@ int gemmul8_b200_product_i32(const gemmul8_b200_args *a, unsigned j, int32_t *C3
 int gemmul8_b200_phase_log_collect(double timers_ns[4], unsigned *calls) {
     PhaseLog &L = g_phase_log;
     if (timers_ns) for (int i = 0; i < 4; ++i) timers_ns[i] = 0.0;
-    if (calls) *calls = (unsigned)L.entries.size();
-    for (auto &e : L.entries) {
-        if (e.n > 0 && cudaEventSynchronize(e.ev[e.n - 1]) != cudaSuccess) return fail(GEMMUL8_ERR_CUDA, "phase log: event synchronise failed");
+    if (calls) *calls = (unsigned)L.ring.size();
+    int rc = GEMMUL8_OK;
+    for (auto &e : L.ring) {
+        if (e.n > 0 && cudaEventSynchronize(e.ev[e.n - 1]) != cudaSuccess) rc = fail(GEMMUL8_ERR_CUDA, "phase log: event synchronise failed");
         double t[4] = {0, 0, 0, 0};
-        PhaseTimer::spans(e.ev, e.n, t);
+        if (rc == GEMMUL8_OK) PhaseTimer::spans(e.ev, e.n, t);
         if (timers_ns) for (int i = 0; i < 4; ++i) timers_ns[i] += t[i];
-        for (auto &ev : e.ev) L.pool.push_back(ev);
+        for (auto ev : e.ev) L.put(ev);
     }
-    L.entries.clear();
+    L.ring.clear();
+    L.head = 0;
+    return rc;
+}
+
+int gemmul8_b200_init(int device) {
+    int count = 0, prev = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(GEMMUL8_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device >= count) return fail(GEMMUL8_ERR_ARGUMENT, "init: no such device");
+    oz::tuning();                                   // environment defaults, once
+    OZ_CUDA(cudaGetDevice(&prev), "get device");
+    if (device >= 0 && device != prev) OZ_CUDA(cudaSetDevice(device), "set device");
+    oz::gemm_prepare_device(/*allow_probe=*/true);  // SM placement table of the pair GEMM (private stream, once per device)
+    if (device >= 0 && device != prev) OZ_CUDA(cudaSetDevice(prev), "set device");
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_set_option(const char *name, int value) {
+    oz::load_options_from_env();
+    oz::Option *o = oz::find_option(name);
+    if (!o) return fail(GEMMUL8_ERR_ARGUMENT, "set_option: unknown option");
+    if (value < o->lo || value > o->hi) return fail(GEMMUL8_ERR_ARGUMENT, "set_option: value out of range");
+    o->value.store(value, std::memory_order_relaxed);
+    return GEMMUL8_OK;
+}
+
+int gemmul8_b200_get_option(const char *name, int *value) {
+    oz::load_options_from_env();
+    oz::Option *o = oz::find_option(name);
+    if (!o || !value) return fail(GEMMUL8_ERR_ARGUMENT, "get_option: unknown option");
+    *value = o->value.load(std::memory_order_relaxed);
     return GEMMUL8_OK;
 }
 

@@ -331,6 +331,12 @@ __device__ __forceinline__ T2 combine_c(int mode, T2 alpha, T2 beta, T2 c, const
     }
 }
 
+template <typename T2> __host__ __device__ inline int alpha_beta_mode_c(T2 alpha, T2 beta) {
+    const bool a1 = alpha.x == 1 && alpha.y == 0, b0 = beta.x == 0 && beta.y == 0, b1 = beta.x == 1 && beta.y == 0;
+    if (a1) return b0 ? AB_10 : b1 ? AB_11 : AB_1B;
+    return b0 ? AB_A0 : b1 ? AB_A1 : AB_AB;
+}
+
 __device__ __forceinline__ uint32_t load4(const uint8_t *p) {
     if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) return *reinterpret_cast<const uint32_t *>(p);
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
@@ -340,7 +346,12 @@ template <typename T2, bool SPLIT, int N>
 __global__ void __launch_bounds__(256) crt_cplx_kernel(size_t m, size_t n, const uint8_t *__restrict__ Cre,
                                                        const uint8_t *__restrict__ Cim, size_t ldc8u, size_t sizeC,
                                                        T2 *__restrict__ C, size_t ldc, const int16_t *__restrict__ sftA,
-                                                       const int16_t *__restrict__ sftB, int mode, T2 alpha, T2 beta) {
+                                                       const int16_t *__restrict__ sftB, int mode, T2 alpha, T2 beta,
+                                                       const T2 *__restrict__ alpha_dev, const T2 *__restrict__ beta_dev) {
+    if (alpha_dev != nullptr) {   // device-resident scalars
+        alpha = *alpha_dev; beta = *beta_dev;
+        mode  = alpha_beta_mode_c(alpha, beta);
+    }
     const size_t row0 = ((size_t)blockIdx.x * 64 + threadIdx.x) * 4;
     const size_t col  = (size_t)blockIdx.y * 4 + threadIdx.y;
     if (row0 >= m || col >= n) return;
@@ -376,30 +387,28 @@ __global__ void __launch_bounds__(256) crt_cplx_kernel(size_t m, size_t n, const
 template <typename T2, bool SPLIT, int N>
 void launch_crt_cplx_one(dim3 grid, dim3 block, cudaStream_t st, size_t m, size_t n, const uint8_t *Cre, const uint8_t *Cim,
                          size_t ldc8u, size_t sizeC, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, int mode,
-                         T2 alpha, T2 beta) {
+                         T2 alpha, T2 beta, const T2 *alpha_dev, const T2 *beta_dev) {
     crt_cplx_kernel<T2, SPLIT, N><<<grid, block, 0, st>>>(m, n, Cre, Cim, ldc8u, sizeC, static_cast<T2 *>(C), ldc, sftA, sftB,
-                                                          mode, alpha, beta);
-}
-
-template <typename T2> int alpha_beta_mode_c(T2 alpha, T2 beta) {
-    const bool a1 = alpha.x == 1 && alpha.y == 0, b0 = beta.x == 0 && beta.y == 0, b1 = beta.x == 1 && beta.y == 0;
-    if (a1) return b0 ? AB_10 : b1 ? AB_11 : AB_1B;
-    return b0 ? AB_A0 : b1 ? AB_A1 : AB_AB;
+                                                          mode, alpha, beta, alpha_dev, beta_dev);
 }
 
 template <typename T2>
 cudaError_t run_crt_cplx(bool split, unsigned N, size_t m, size_t n, const uint8_t *Cre, const uint8_t *Cim, size_t ldc8u,
-                         size_t sizeC, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha_host,
-                         const void *beta_host, cudaStream_t st) {
-    const T2 alpha = *static_cast<const T2 *>(alpha_host), beta = *static_cast<const T2 *>(beta_host);
+                         size_t sizeC, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha_p,
+                         const void *beta_p, bool device_scalars, cudaStream_t st) {
+    const T2 *alpha_dev = device_scalars ? static_cast<const T2 *>(alpha_p) : nullptr;
+    const T2 *beta_dev  = device_scalars ? static_cast<const T2 *>(beta_p) : nullptr;
+    T2 alpha{}, beta{};
+    alpha.x = 1;
+    if (!device_scalars) { alpha = *static_cast<const T2 *>(alpha_p); beta = *static_cast<const T2 *>(beta_p); }
     const int mode = alpha_beta_mode_c(alpha, beta);
     dim3 block(64, 4), grid((unsigned)(((m + 3) / 4 + 63) / 64), (unsigned)((n + 3) / 4));
 #define OZ_CRT_CASE(NN)                                                                                                           \
     case NN:                                                                                                                      \
         if constexpr (NN >= 8 && sizeof(T2) == 16) {                                                                              \
-            if (split) { launch_crt_cplx_one<T2, true, NN>(grid, block, st, m, n, Cre, Cim, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta); break; } \
+            if (split) { launch_crt_cplx_one<T2, true, NN>(grid, block, st, m, n, Cre, Cim, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta, alpha_dev, beta_dev); break; } \
         }                                                                                                                         \
-        launch_crt_cplx_one<T2, false, NN>(grid, block, st, m, n, Cre, Cim, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta);  \
+        launch_crt_cplx_one<T2, false, NN>(grid, block, st, m, n, Cre, Cim, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta, alpha_dev, beta_dev);  \
         break;
     switch (N) {
         OZ_CRT_CASE(2) OZ_CRT_CASE(3) OZ_CRT_CASE(4) OZ_CRT_CASE(5) OZ_CRT_CASE(6) OZ_CRT_CASE(7) OZ_CRT_CASE(8)
@@ -482,12 +491,12 @@ cudaError_t launch_bound_extract_complex(int dtype, bool strided, const void *X,
 
 cudaError_t launch_crt_complex(int dtype_C, bool split_weights, unsigned num_moduli, size_t m, size_t n, const uint8_t *C8u_re,
                                const uint8_t *C8u_im, size_t ldc8u, size_t sizeC, void *C, size_t ldc, const int16_t *sftA,
-                               const int16_t *sftB, const void *alpha_host, const void *beta_host, cudaStream_t st) {
+                               const int16_t *sftB, const void *alpha_p, const void *beta_p, bool device_scalars, cudaStream_t st) {
     if (m == 0 || n == 0) return cudaSuccess;
     if ((n + 3) / 4 > 65535) return cudaErrorInvalidValue;
     switch (dtype_C) {
-        case DT_C64: return run_crt_cplx<double2>(split_weights, num_moduli, m, n, C8u_re, C8u_im, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_host, beta_host, st);
-        case DT_C32: return run_crt_cplx<float2>(false, num_moduli, m, n, C8u_re, C8u_im, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_host, beta_host, st);
+        case DT_C64: return run_crt_cplx<double2>(split_weights, num_moduli, m, n, C8u_re, C8u_im, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_p, beta_p, device_scalars, st);
+        case DT_C32: return run_crt_cplx<float2>(false, num_moduli, m, n, C8u_re, C8u_im, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_p, beta_p, device_scalars, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -22,7 +22,12 @@ template <typename T, bool SPLIT, int N>
 __global__ void __launch_bounds__(256) crt_kernel(size_t m, size_t n, const uint8_t *__restrict__ C8u, size_t ldc8u,
                                                   size_t sizeC, T *__restrict__ C, size_t ldc,
                                                   const int16_t *__restrict__ sftA, const int16_t *__restrict__ sftB,
-                                                  int mode, T alpha, T beta) {
+                                                  int mode, T alpha, T beta, const T *__restrict__ alpha_dev,
+                                                  const T *__restrict__ beta_dev) {
+    if (alpha_dev != nullptr) {   // CUBLAS_POINTER_MODE_DEVICE-style scalars: read here, never on the host
+        alpha = *alpha_dev; beta = *beta_dev;
+        mode  = alpha_beta_mode(alpha, beta);
+    }
     const size_t row0 = ((size_t)blockIdx.x * 64 + threadIdx.x) * 4;
     const size_t col  = (size_t)blockIdx.y * 4 + threadIdx.y;
     if (row0 >= m || col >= n) return;
@@ -83,23 +88,27 @@ __global__ void __launch_bounds__(256) crt_kernel(size_t m, size_t n, const uint
 
 template <typename T, bool SPLIT, int N>
 void launch_one(dim3 grid, dim3 block, cudaStream_t st, size_t m, size_t n, const uint8_t *C8u, size_t ldc8u, size_t sizeC,
-                void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, int mode, T alpha, T beta) {
-    crt_kernel<T, SPLIT, N><<<grid, block, 0, st>>>(m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta);
+                void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB, int mode, T alpha, T beta, const T *alpha_dev,
+                const T *beta_dev) {
+    crt_kernel<T, SPLIT, N><<<grid, block, 0, st>>>(m, n, C8u, ldc8u, sizeC, static_cast<T *>(C), ldc, sftA, sftB, mode, alpha, beta,
+                                                    alpha_dev, beta_dev);
 }
 
 template <typename T>
 cudaError_t run_crt(bool split, unsigned N, size_t m, size_t n, const uint8_t *C8u, size_t ldc8u, size_t sizeC, void *C,
-                    size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha_host, const void *beta_host,
-                    cudaStream_t st) {
-    const T alpha = *static_cast<const T *>(alpha_host), beta = *static_cast<const T *>(beta_host);
+                    size_t ldc, const int16_t *sftA, const int16_t *sftB, const void *alpha_p, const void *beta_p,
+                    bool device_scalars, cudaStream_t st) {
+    const T *alpha_dev = device_scalars ? static_cast<const T *>(alpha_p) : nullptr;
+    const T *beta_dev  = device_scalars ? static_cast<const T *>(beta_p) : nullptr;
+    const T alpha = device_scalars ? T(1) : *static_cast<const T *>(alpha_p), beta = device_scalars ? T(0) : *static_cast<const T *>(beta_p);
     const int mode = alpha_beta_mode(alpha, beta);
     dim3 block(64, 4), grid((unsigned)(((m + 3) / 4 + 63) / 64), (unsigned)((n + 3) / 4));
 #define OZ_CRT_CASE(NN)                                                                                                          \
     case NN:                                                                                                                     \
         if constexpr (NN >= 8 && sizeof(T) == 8) {                                                                               \
-            if (split) { launch_one<T, true, NN>(grid, block, st, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta); break; } \
+            if (split) { launch_one<T, true, NN>(grid, block, st, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta, alpha_dev, beta_dev); break; } \
         }                                                                                                                        \
-        launch_one<T, false, NN>(grid, block, st, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta);               \
+        launch_one<T, false, NN>(grid, block, st, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, mode, alpha, beta, alpha_dev, beta_dev); \
         break;
     switch (N) {
         OZ_CRT_CASE(2) OZ_CRT_CASE(3) OZ_CRT_CASE(4) OZ_CRT_CASE(5) OZ_CRT_CASE(6) OZ_CRT_CASE(7) OZ_CRT_CASE(8)
@@ -117,7 +126,9 @@ cudaError_t run_crt(bool split, unsigned N, size_t m, size_t n, const uint8_t *C
 namespace {
 // k == 0: the product is empty, C = beta * C (BLAS: C is not read when beta == 0)
 template <typename T>
-__global__ void scale_c_kernel(size_t m, size_t n, T *__restrict__ C, size_t ldc, T beta_re, T beta_im, bool cplx) {
+__global__ void scale_c_kernel(size_t m, size_t n, T *__restrict__ C, size_t ldc, T beta_re, T beta_im, bool cplx,
+                               const T *__restrict__ beta_dev) {
+    if (beta_dev != nullptr) { beta_re = beta_dev[0]; beta_im = cplx ? beta_dev[1] : T(0); }
     const size_t w = cplx ? 2 * m : m;                 // scalars per column
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
     if (i >= w) return;
@@ -131,17 +142,20 @@ __global__ void scale_c_kernel(size_t m, size_t n, T *__restrict__ C, size_t ldc
 }
 }  // namespace
 
-cudaError_t launch_scale_c(int dtype_C, size_t m, size_t n, void *C, size_t ldc, const void *beta_host, cudaStream_t st) {
+cudaError_t launch_scale_c(int dtype_C, size_t m, size_t n, void *C, size_t ldc, const void *beta_p, bool device_scalars,
+                           cudaStream_t st) {
     if (m == 0 || n == 0) return cudaSuccess;
     if (n > 65535) return cudaErrorInvalidValue;
     const bool cplx = dtype_C == DT_C32 || dtype_C == DT_C64;
     dim3 grid((unsigned)(((cplx ? 2 * m : m) + 255) / 256), (unsigned)n);
     if (dtype_C == DT_F64 || dtype_C == DT_C64) {
-        const double *b = static_cast<const double *>(beta_host);
-        scale_c_kernel<double><<<grid, 256, 0, st>>>(m, n, static_cast<double *>(C), ldc, b[0], cplx ? b[1] : 0.0, cplx);
+        const double *b = static_cast<const double *>(beta_p);
+        if (device_scalars) scale_c_kernel<double><<<grid, 256, 0, st>>>(m, n, static_cast<double *>(C), ldc, 0.0, 0.0, cplx, b);
+        else scale_c_kernel<double><<<grid, 256, 0, st>>>(m, n, static_cast<double *>(C), ldc, b[0], cplx ? b[1] : 0.0, cplx, nullptr);
     } else {
-        const float *b = static_cast<const float *>(beta_host);
-        scale_c_kernel<float><<<grid, 256, 0, st>>>(m, n, static_cast<float *>(C), ldc, b[0], cplx ? b[1] : 0.f, cplx);
+        const float *b = static_cast<const float *>(beta_p);
+        if (device_scalars) scale_c_kernel<float><<<grid, 256, 0, st>>>(m, n, static_cast<float *>(C), ldc, 0.f, 0.f, cplx, b);
+        else scale_c_kernel<float><<<grid, 256, 0, st>>>(m, n, static_cast<float *>(C), ldc, b[0], cplx ? b[1] : 0.f, cplx, nullptr);
     }
     count_launch();
     return cudaGetLastError();
@@ -149,12 +163,12 @@ cudaError_t launch_scale_c(int dtype_C, size_t m, size_t n, void *C, size_t ldc,
 
 cudaError_t launch_crt(int dtype_C, bool split_weights, unsigned num_moduli, size_t m, size_t n, const uint8_t *C8u,
                        size_t ldc8u, size_t sizeC, void *C, size_t ldc, const int16_t *sftA, const int16_t *sftB,
-                       const void *alpha_host, const void *beta_host, cudaStream_t st) {
+                       const void *alpha_p, const void *beta_p, bool device_scalars, cudaStream_t st) {
     if (m == 0 || n == 0) return cudaSuccess;
     if ((n + 3) / 4 > 65535) return cudaErrorInvalidValue;
     switch (dtype_C) {
-        case DT_F64: return run_crt<double>(split_weights, num_moduli, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_host, beta_host, st);
-        case DT_F32: return run_crt<float>(false, num_moduli, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_host, beta_host, st);
+        case DT_F64: return run_crt<double>(split_weights, num_moduli, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_p, beta_p, device_scalars, st);
+        case DT_F32: return run_crt<float>(false, num_moduli, m, n, C8u, ldc8u, sizeC, C, ldc, sftA, sftB, alpha_p, beta_p, device_scalars, st);
     }
     return cudaErrorInvalidValue;
 }

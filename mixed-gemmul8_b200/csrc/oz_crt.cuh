@@ -7,11 +7,16 @@
 #pragma once
 #include "oz_common.cuh"
 
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+
 namespace oz {
 
 enum AlphaBeta : int { AB_10 = 0, AB_11, AB_1B, AB_A0, AB_A1, AB_AB };
 
-template <typename T> inline int alpha_beta_mode(T alpha, T beta) {
+template <typename T> __host__ __device__ inline int alpha_beta_mode(T alpha, T beta) {
     if (alpha == T(1)) return (beta == T(0)) ? AB_10 : (beta == T(1)) ? AB_11 : AB_1B;
     return (beta == T(0)) ? AB_A0 : (beta == T(1)) ? AB_A1 : AB_AB;
 }

@@ -39,6 +39,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include <cudaTypedefs.h>
@@ -86,12 +87,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The bound is wall time
+// (%globaltimer), 20 s: far beyond anything a time-sliced or co-scheduled kernel can be held up for, so it only ever
+// fires on a genuine deadlock.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+        if ((++spins & 0xfffu) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
@@ -181,22 +194,13 @@ struct KernelArgs {
     // EPI_CRT
     void *C; size_t ldc;
     const int16_t *sftA; const int16_t *sftB;
-    double alpha, beta; int ab_mode; int debug_skip_crt;
-    uint32_t cta_map, num_sms;
+    double alpha, beta; int ab_mode;
 };
 
 // the it-th work item of this CTA; false when the CTA has run out of work
-__device__ __forceinline__ uint32_t virtual_cta(const KernelArgs &a) {
-    if (a.cta_map == 0 || gridDim.x != a.num_sms) return blockIdx.x;   // experiment knob OZ_MAP: work by SM id instead of block id
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (a.cta_map == 1) return smid;
-    if (a.cta_map == 2) return (smid & 1u) * (a.num_sms / 2) + (smid >> 1);       // TPC siblings far apart
-    return (smid % 8u) * ((a.num_sms + 7) / 8) + smid / 8u < a.num_sms ? (smid % 8u) * ((a.num_sms + 7) / 8) + smid / 8u : smid;
-}
 __device__ __forceinline__ bool next_work(const KernelArgs &a, uint32_t it, uint32_t &tm, uint32_t &tn, uint32_t &j) {
     uint32_t unit, jj = 0;
-    const uint32_t vb = virtual_cta(a);
+    const uint32_t vb = blockIdx.x;
     if (a.tile_major) {
         const uint32_t t = it / a.num_slices;
         jj   = it - t * a.num_slices;
@@ -307,14 +311,9 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * SMEM_STAGE;
-                    if (args.debug_skip_crt == 2 && (kb & 1)) {   // tuning experiment: what if half of the B traffic were shared?
-                        mbar_expect_tx(full_bar(stage), SMEM_A);
-                        tma_load_3d(sa, &map_a, full_bar(stage), (int)(kb * BLOCK_K), (int)(tm * BLOCK_M), (int)j);
-                    } else {
                     mbar_expect_tx(full_bar(stage), SMEM_STAGE);
                     tma_load_3d(sa, &map_a, full_bar(stage), (int)(kb * BLOCK_K), (int)(tm * BLOCK_M), (int)j);
                     tma_load_3d(sa + SMEM_A, &map_b, full_bar(stage), (int)(kb * BLOCK_K), (int)(tn * BLOCK_N), (int)j);
-                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -482,7 +481,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const uint32_t row0 = tm * BLOCK_M + 4 * lane;
                 const uint32_t col0 = tn * BLOCK_N;
                 const uint32_t ncol = min((uint32_t)BLOCK_N, args.rowsB - col0);
-                if (row0 < args.rowsA && !args.debug_skip_crt) {
+                if (row0 < args.rowsA) {
                     int sa[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) sa[e] = (row0 + e < args.rowsA) ? (int)args.sftA[row0 + e] : 0;
@@ -644,8 +643,8 @@ struct PairArgs {
     PairSched sched;
     uint8_t *C8u; size_t ldc8u, sizeC;
     int combine; uint8_t *C8u_aux;
-    uint32_t debug_skew;
-    const uint32_t *slot;   // smid -> block index of a plain launch (nullptr: use blockIdx)
+    const uint32_t *slot;   // smid -> block index of a plain launch (nullptr: work goes by blockIdx)
+    uint32_t *claims;       // with `slot`: one word per pair, zeroed before the launch
 };
 
 template <bool RMW, int NSTAGES>
@@ -663,19 +662,31 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank    = cluster_ctarank();         // 0 = leader
-    // Work goes by PLACEMENT, not by block index: a cluster launch fills the SMs GPC by GPC, which would put all pairs
-    // that share a B panel behind one GPC port (measured: +5 ms from that alone).  slot[smid] is the block index a plain
-    // launch gives this SM (TPC by TPC, round-robin over the GPCs), so the sharers end up spread exactly as in the
-    // single-CTA kernel.
-    uint32_t pair = blockIdx.x >> 1;
-    if (args.slot != nullptr) {
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        pair = args.slot[smid] >> 1;
-    }
     const uint32_t npairs = gridDim.x >> 1;
     const uint32_t num_kb  = args.num_kb;
     const uint32_t total   = args.sched.total;
+    // Work goes by PLACEMENT, not by block index: a cluster launch fills the SMs GPC by GPC, which would put all pairs
+    // that share a B panel behind one GPC port (measured: +5 ms from that alone).  slot[smid] is the block index a plain
+    // launch gives this SM (TPC by TPC, round-robin over the GPCs), so the sharers end up spread exactly as in the
+    // single-CTA kernel.  The SM id is only a PREFERENCE: nothing guarantees one cluster per TPC (another kernel may hold an
+    // SM, so that two clusters of this launch run on the same TPC one after the other), therefore every cluster CLAIMS its
+    // slot in a per-launch table and takes the next free one if the preferred slot is gone.  npairs clusters, npairs
+    // slots: each slot is worked exactly once whatever the placement.
+    const uint32_t pair_slot = bar_base + 8u * (2 * NSTAGES + 5);
+    if (warp == 1 && lane == 0 && rank == 0) {
+        uint32_t pair = blockIdx.x >> 1;
+        if (args.slot != nullptr) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            uint32_t want = args.slot[smid] >> 1;
+            if (want >= npairs) want = pair;
+            for (uint32_t i = 0; i < npairs; ++i) {
+                const uint32_t c = want + i < npairs ? want + i : want + i - npairs;
+                if (atomicCAS(args.claims + c, 0u, 1u) == 0u) { pair = c; break; }
+            }
+        }
+        asm volatile("st.shared::cta.u32 [%0], %1;" ::"r"(pair_slot), "r"(pair) : "memory");   // read by both CTAs after the cluster barrier
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -694,12 +705,13 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     cluster_sync_all();          // barriers of both CTAs are initialised before anybody signals across the pair
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    uint32_t pair;               // the leader's claim (its CTA stays resident until the cluster barrier at the end)
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(pair) : "r"(map_to_cta(pair_slot, 0)) : "memory");
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, tm, tn, j;
-            if (args.debug_skew) __nanosleep((pair % args.sched.band_m) * args.debug_skew);   // experiment: break the lockstep of the sharers
             for (uint32_t item = pair; item < total; item += npairs) {
                 args.sched.decode(item, tm, tn, j);
                 const int rowA = (int)(tm * 256 + rank * 128), rowB = (int)(tn * BLOCK_N + rank * 128);
@@ -907,9 +919,9 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     a.first_modulus = p.first_modulus;
     a.num_slices = p.num_slices;
     a.tile_major = tile_major ? 1u : 0u;
-    const char *be = getenv("OZ_BAND");   // tuning knob: row tiles per scheduling band
+    const int band = tuning().band;
     a.sched.init((uint32_t)((p.rowsA + BLOCK_M - 1) / BLOCK_M), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N),
-                 tile_major ? 1u : p.num_slices, be ? (uint32_t)atoi(be) : (uint32_t)BAND_M);
+                 tile_major ? 1u : p.num_slices, band > 0 ? (uint32_t)band : (uint32_t)BAND_M);
     a.C = p.C; a.ldc = p.ldc; a.sftA = p.sftA; a.sftB = p.sftB; a.alpha = p.alpha; a.beta = p.beta;
     a.ab_mode = alpha_beta_mode(p.alpha, p.beta);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
@@ -920,10 +932,20 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     return a;
 }
 
-int sm_count() {   // of the current device
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+constexpr int kMaxDevices = 64;
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+int sm_count() {   // of the current device (cached: an attribute query per launch is measurable at 60 us per call)
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return 0;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
     return n;
 }
 
@@ -932,28 +954,11 @@ cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, BLOCK_M)) return cudaErrorInvalidValue;
     if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, BLOCK_N)) return cudaErrorInvalidValue;
-    const char *dbg = getenv("OZ_DEBUG_SCHED");   // tuning knob: "tile" forces the tile-major schedule, "skipcrt" idles the CRT warps
-    KernelArgs a = make_args(p, EPI == EPI_CRT || (dbg && strstr(dbg, "tile")));
-    a.debug_skip_crt = (dbg && strstr(dbg, "skipcrt")) ? 1 : (dbg && strstr(dbg, "halfb")) ? 2 : 0;
-    const char *mp = getenv("OZ_MAP");
-    a.cta_map = mp ? (uint32_t)atoi(mp) : 0u;
-    a.num_sms = (uint32_t)sm_count();
+    KernelArgs a = make_args(p, EPI == EPI_CRT);
     auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT, RMW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
-    const char *cl = getenv("OZ_CLUSTER");   // experiment: the same kernel launched as clusters of 2 (placement effect on L2)
-    if (cl && atoi(cl) == 2 && grid % 2 == 0) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_TOTAL; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, a);
-        count_launch();
-        return le != cudaSuccess ? le : cudaGetLastError();
-    }
     kern<<<grid, NUM_THREADS, SMEM_TOTAL, st>>>(ma, mb, a);
     count_launch();
     return cudaGetLastError();
@@ -971,6 +976,8 @@ cudaError_t launch_simt_t(const GemmProblem &p, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 // placement probe: which block index does a plain 1-CTA-per-SM launch give each SM?
+// Runs once per device, on a private stream, from gemmul8_b200_init() or from the first gemm call that is not being
+// captured into a graph; never on the caller's stream, never with a device-wide synchronisation.
 // ---------------------------------------------------------------------------------------------
 __global__ void placement_probe_kernel(uint32_t *slot) {
     extern __shared__ uint8_t probe_smem[];
@@ -982,72 +989,85 @@ __global__ void placement_probe_kernel(uint32_t *slot) {
 }
 const uint32_t *probe_placement(int n) {
     uint32_t *d = nullptr;
-    if (cudaMalloc(&d, sizeof(uint32_t) * (size_t)n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    cudaDeviceSynchronize();
-    cudaMemset(d, 0xff, sizeof(uint32_t) * (size_t)n);
-    cudaFuncSetAttribute(placement_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    placement_probe_kernel<<<n, 32, 200 * 1024>>>(d);
+    cudaStream_t ps = nullptr;
+    if (cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMalloc(&d, sizeof(uint32_t) * (size_t)n) != cudaSuccess) { cudaGetLastError(); cudaStreamDestroy(ps); return nullptr; }
     std::vector<uint32_t> h((size_t)n), seen((size_t)n, 0);
-    if (cudaMemcpy(h.data(), d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
-    bool ok = true;
-    for (int i = 0; i < n; ++i) { if (h[i] >= (uint32_t)n || seen[h[i]]++) ok = false; }
-    for (int i = 0; i + 1 < n; i += 2) ok = ok && (h[i] >> 1) == (h[i + 1] >> 1);   // TPC siblings hold consecutive blocks
-    if (!ok) { cudaFree(d); return nullptr; }
-    return d;                           // lives as long as the process
+    bool ok = cudaMemsetAsync(d, 0xff, sizeof(uint32_t) * (size_t)n, ps) == cudaSuccess &&
+              cudaFuncSetAttribute(placement_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+    if (ok) {
+        placement_probe_kernel<<<n, 32, 200 * 1024, ps>>>(d);
+        ok = cudaMemcpyAsync(h.data(), d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ps) == cudaSuccess &&
+             cudaStreamSynchronize(ps) == cudaSuccess;
+    }
+    cudaStreamDestroy(ps);
+    // a permutation, with TPC siblings holding consecutive blocks -- anything else (busy GPU, MIG slice, ...): no table
+    for (int i = 0; ok && i < n; ++i) { if (h[i] >= (uint32_t)n || seen[h[i]]++) ok = false; }
+    for (int i = 0; ok && i + 1 < n; i += 2) ok = (h[i] >> 1) == (h[i + 1] >> 1);
+    if (!ok) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    return d;                           // n words, kept for the life of the process
 }
-// per device, probed once (thread-safe); nullptr if the probe did not produce a permutation (busy GPU, MIG, ...)
-const uint32_t *placement_slots() {
-    constexpr int kMaxDevices = 64;
-    static std::once_flag once[kMaxDevices];
-    static const uint32_t *table[kMaxDevices] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
-    std::call_once(once[dev], [dev] {
-        int n = 0;
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        table[dev] = n > 0 ? probe_placement(n) : nullptr;
-    });
-    return table[dev];
+struct Placement { std::mutex mu; std::atomic<int> state{0}; const uint32_t *table = nullptr; };   // state: 0 unknown, 1 probed
+Placement g_placement[kMaxDevices];
+
+const uint32_t *placement_slots(bool allow_probe) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return nullptr;
+    Placement &P = g_placement[dev];
+    if (P.state.load(std::memory_order_acquire) == 1) return P.table;
+    if (!allow_probe) return nullptr;
+    std::lock_guard<std::mutex> lock(P.mu);
+    if (P.state.load(std::memory_order_acquire) == 0) {
+        const int n = sm_count();
+        P.table = (n >= 2 && !(n & 1)) ? probe_placement(n) : nullptr;
+        P.state.store(1, std::memory_order_release);
+    }
+    return P.table;
 }
 
 // CTA-pair kernel for EPI_RESIDUE (all combine modes).  Default whenever the placement table exists (whole GPU, even SM
-// count); OZ_GEMM_PAIR=0 selects the single-CTA kernel, OZ_GEMM_PAIR=1 forces the pair kernel even without the table.
+// count); option gemm_pair = 0 selects the single-CTA kernel, 1 forces the pair kernel even without the table.
 // Measured at 16384^3, 14 moduli, same box: single-CTA 46.7 / 48.7 ms, pairs placed by block index 53.9 - 57.2 ms,
 // pairs placed like a plain launch 44.7 / 45.2 ms (profiles/r01_pair_kernel_notes.md).
-bool pair_kernel_enabled() {
-    const char *e = getenv("OZ_GEMM_PAIR");
-    if (e && e[0] == '0') return false;
+bool pair_kernel_enabled(cudaStream_t st) {
+    const int mode = tuning().gemm_pair;
+    if (mode == 0) return false;
     if (sm_count() < 2 || (sm_count() & 1)) return false;
-    if (e && e[0] == '1') return true;
-    return placement_slots() != nullptr;
+    if (mode == 1) return true;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+    return placement_slots(!capturing) != nullptr;
 }
 template <bool RMW>
 cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, 128)) return cudaErrorInvalidValue;
     if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, 128)) return cudaErrorInvalidValue;
+    const Tuning tn = tuning();
     PairArgs a{};
     a.rowsA = (uint32_t)p.rowsA; a.rowsB = (uint32_t)p.rowsB;
     a.num_kb = (uint32_t)((p.ld8i + BLOCK_K - 1) / BLOCK_K);
     a.first_modulus = p.first_modulus;
     a.rows_store = (uint32_t)((p.rowsA + 3) / 4 * 4);
-    const char *be = getenv("OZ_PAIR_BAND");
     a.sched.init((uint32_t)((p.rowsA + 255) / 256), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N), p.num_slices,
-                 be ? (uint32_t)atoi(be) : (uint32_t)PAIR_BAND);
+                 tn.pair_band > 0 ? (uint32_t)tn.pair_band : (uint32_t)PAIR_BAND);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
     a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
-    const char *sk = getenv("OZ_PAIR_SKEW");
-    a.debug_skew = sk ? (uint32_t)atoi(sk) : 0u;
-    const char *se = getenv("OZ_PAIR_STAGES");   // tuning knob
-    const int stages = se ? atoi(se) : p.share_sm ? 4 : PAIR_STAGES;
+    const int stages = tn.pair_stages ? tn.pair_stages : p.share_sm ? 4 : PAIR_STAGES;
     auto kern = stages == 4 ? oz_gemm_pair_kernel<RMW, 4> : stages == 5 ? oz_gemm_pair_kernel<RMW, 5> : oz_gemm_pair_kernel<RMW, 6>;
     const int smem_bytes = pair_smem_total(stages == 4 ? 4 : stages == 5 ? 5 : 6);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const uint32_t max_pairs = (uint32_t)sm_count() / 2;
     const uint32_t pairs = a.sched.total < max_pairs ? a.sched.total : max_pairs;
-    const char *pm = getenv("OZ_PAIR_MAP");
-    a.slot = (pairs == max_pairs && (uint32_t)sm_count() == 2 * max_pairs && !(pm && pm[0] == '0')) ? placement_slots() : nullptr;
+    // work by placement needs one cluster per TPC slot AND the per-launch claim table; without either, by block index
+    static_assert(kClaimBytes >= sizeof(uint32_t) * 128, "claim table: one word per pair");
+    a.slot = (pairs == max_pairs && p.claims != nullptr && max_pairs <= kClaimBytes / sizeof(uint32_t)) ? placement_slots(false) : nullptr;
+    a.claims = p.claims;
+    if (a.slot != nullptr) {
+        e = cudaMemsetAsync(p.claims, 0, sizeof(uint32_t) * max_pairs, st);
+        if (e != cudaSuccess) return e;
+    }
     kern<<<2 * pairs, PAIR_THREADS, smem_bytes, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
     count_launch();
     return cudaGetLastError();
@@ -1055,11 +1075,15 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
 
 }  // namespace
 
+void gemm_prepare_device(bool allow_probe) {
+    if (tuning().gemm_pair != 0) placement_slots(allow_probe);
+}
+
 cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStream_t st) {
     if (p.rowsA == 0 || p.rowsB == 0 || p.num_slices == 0) return cudaSuccess;
     switch (epi) {
         case EPI_RESIDUE:
-            if (pair_kernel_enabled()) return p.combine == RC_STORE ? launch_pair<false>(p, st) : launch_pair<true>(p, st);
+            if (pair_kernel_enabled(st)) return p.combine == RC_STORE ? launch_pair<false>(p, st) : launch_pair<true>(p, st);
             return p.combine == RC_STORE ? launch_tc<EPI_RESIDUE>(p, st) : launch_tc<EPI_RESIDUE, double, false, true>(p, st);
         case EPI_INT32:   return launch_tc<EPI_INT32>(p, st);
         case EPI_ABSMAX:  return launch_tc<EPI_ABSMAX>(p, st);

@@ -7,7 +7,8 @@
 // same idea for its comparison library (ozIMMU_EF/src/cublas.cu:135-310: hijacked cublasGemmEx /
 // cublasDgemm with an environment-variable mode switch).  Nothing here computes: a call is either
 // forwarded to gemmul8_b200_gemm (include/gemmul8_b200.h) on the handle's stream, or passed on to the
-// real cuBLAS (small problems, device pointer mode, k > 2^17, unsupported types).
+// real cuBLAS (small problems, k > 2^17, unsupported types).  CUBLAS_POINTER_MODE_DEVICE is honoured: alpha / beta are then
+// handed through as device pointers (GEMMUL8_FLAG_DEVICE_SCALARS) and read by the CRT kernel.
 //
 // Environment:
 //   GEMMUL8_NUM_MODULI_D / _S   moduli for fp64 / fp32 results (default 14 / 6; the reference's headline settings)
@@ -57,16 +58,20 @@ struct Config {
 };
 const Config &config() { static Config c; return c; }
 
-// one growing workspace per device, serialised by a mutex (cuBLAS handles are per-thread, calls on one
-// stream are ordered; a second stream using the buffer concurrently is ordered by the event below)
+// one growing workspace PER DEVICE, each with its own mutex and its own event (created on that device): calls on one
+// stream are ordered by the stream, a second stream using the buffer is ordered behind the previous call by the event
 struct Workspace {
     std::mutex mu;
     void *ptr = nullptr;
     size_t bytes = 0;
     cudaEvent_t last = nullptr;
-    int device = -1;
+    bool recorded = false;
 };
-Workspace &workspace() { static Workspace w; return w; }
+constexpr int kMaxDevices = 64;
+Workspace *workspace(int dev) {
+    static Workspace w[kMaxDevices];
+    return (dev >= 0 && dev < kMaxDevices) ? &w[dev] : nullptr;
+}
 
 std::atomic<unsigned long long> g_intercepted{0};
 
@@ -83,7 +88,7 @@ bool emulate(cublasHandle_t handle, cublasOperation_t ta, cublasOperation_t tb, 
     static auto get_mode = next_symbol<cublasStatus_t (*)(cublasHandle_t, cublasPointerMode_t *)>("cublasGetPointerMode_v2");
     static auto get_stream = next_symbol<cublasStatus_t (*)(cublasHandle_t, cudaStream_t *)>("cublasGetStream_v2");
     cublasPointerMode_t mode;
-    if (get_mode(handle, &mode) != CUBLAS_STATUS_SUCCESS || mode != CUBLAS_POINTER_MODE_HOST) return false;
+    if (get_mode(handle, &mode) != CUBLAS_STATUS_SUCCESS) return false;
     cudaStream_t st = nullptr;
     if (get_stream(handle, &st) != CUBLAS_STATUS_SUCCESS) return false;
 
@@ -96,19 +101,22 @@ bool emulate(cublasHandle_t handle, cublasOperation_t ta, cublasOperation_t tb, 
     a.compute_type = cplx ? cfg.complex_type : GEMMUL8_REAL_DEFAULT;
     a.dtype_A = a.dtype_B = a.dtype_C = dtype;
     a.stream = st;
+    if (mode == CUBLAS_POINTER_MODE_DEVICE) a.flags |= GEMMUL8_FLAG_DEVICE_SCALARS;
     size_t need = gemmul8_b200_worksize(a.m, a.n, a.k, a.num_moduli, a.compute_type);
 
-    Workspace &w = workspace();
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    Workspace *wp = workspace(dev);
+    if (!wp) return false;
+    Workspace &w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
-    int dev = 0;
-    cudaGetDevice(&dev);
     // The full workspace (N (m + n) k bytes and more) may not fit beside the application's matrices, or may exceed the
     // configured cap: real types then take the low-memory call with the largest blocks that do fit (same bits of C).
     size_t block_rows = 0, block_cols = 0, budget = cfg.max_work;
-    if (w.device != dev || w.bytes < need) {
+    if (w.bytes < need) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t avail = (free_b + (w.device == dev ? w.bytes : 0)) / 10 * 9;   // what a re-allocation could get
+            const size_t avail = (free_b + w.bytes) / 10 * 9;   // what a re-allocation could get
             if (!budget || avail < budget) budget = avail;
         }
     }
@@ -116,17 +124,23 @@ bool emulate(cublasHandle_t handle, cublasOperation_t ta, cublasOperation_t tb, 
         if (cplx || gemmul8_b200_plan_blocks(a.m, a.n, a.k, a.num_moduli, budget, &block_rows, &block_cols, &need) != GEMMUL8_OK)
             return false;                                  // nothing fits: let cuBLAS do it
     }
-    if (w.device != dev || w.bytes < need) {
-        if (w.ptr) { cudaDeviceSynchronize(); cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; }
+    if (!w.last && cudaEventCreateWithFlags(&w.last, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); w.last = nullptr; return false; }
+    if (w.bytes < need) {
+        // grow: the previous call on this device (the only user of the old buffer) must have finished with it
+        if (w.ptr) {
+            if (w.recorded && cudaEventSynchronize(w.last) != cudaSuccess) { cudaGetLastError(); return false; }
+            cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0;
+        }
         if (cudaMalloc(&w.ptr, need) != cudaSuccess) { cudaGetLastError(); w.ptr = nullptr; return false; }   // no room: let cuBLAS do it
-        w.bytes = need; w.device = dev;
-        if (!w.last) cudaEventCreateWithFlags(&w.last, cudaEventDisableTiming);
-    } else if (w.last) {
-        cudaStreamWaitEvent(st, w.last, 0);   // another stream may still be using the buffer
+        w.bytes = need;
+    } else if (w.recorded) {
+        if (cudaStreamWaitEvent(st, w.last, 0) != cudaSuccess) { cudaGetLastError(); return false; }   // another stream may still be using the buffer
     }
     a.work = w.ptr;
     const int rc = block_rows ? gemmul8_b200_gemm_blocked(&a, block_rows, block_cols) : gemmul8_b200_gemm(&a);
-    if (w.last) cudaEventRecord(w.last, st);
+    // whatever was enqueued (a refused call may have enqueued part of its work) is ordered before the next user
+    if (cudaEventRecord(w.last, st) == cudaSuccess) w.recorded = true;
+    else { cudaGetLastError(); cudaStreamSynchronize(st); w.recorded = false; }
     if (rc != GEMMUL8_OK) {
         if (cfg.verbose) fprintf(stderr, "gemmul8_b200_blas: emulation refused (%s), falling back to cuBLAS\n", gemmul8_b200_last_error());
         return false;

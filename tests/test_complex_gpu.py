@@ -202,7 +202,7 @@ def test_no_writes_outside_workspace_and_c(g, monkeypatch):
     for ct in (BIG, CLASSIC, KARA):
         cases += [(131, 70, 101, 9, True, 0, 2, torch.complex128, ct, 0), (70, 53, 100, 8, False, 1, 0, torch.complex64, ct, 0)]
     for pair in ("0", "1"):
-        monkeypatch.setenv("OZ_GEMM_PAIR", pair)
+        g.set_option("gemm_pair", int(pair))
         for (m, n, k, N, fast, opA, opB, dt, ct, flags) in cases:
             A, B = operands(g, m, n, k, opA, opB, dt, dt)
             ws = g.workSize(m, n, k, N, ct)
@@ -217,4 +217,4 @@ def test_no_writes_outside_workspace_and_c(g, monkeypatch):
             check(wbuf, woff, ws, ("work", m, n, k, N, ct, pair))
             check(cbuf, coff, m * n * es, ("C", m, n, k, N, ct, pair))
             assert torch.isfinite(torch.view_as_real(C) if C.is_complex() else C).all()
-    monkeypatch.delenv("OZ_GEMM_PAIR", raising=False)
+    g.set_option("gemm_pair", -1)

@@ -237,16 +237,16 @@ def test_fused_crt_equals_unfused(g, m, n, k, N, dt, alpha, beta):
 
 def test_encoder_routes_equal_reference_instruction_sequence(g, monkeypatch):
     """The short exact residue routes of the encoders (oz_residue.cuh) against the reference's own
-    rint / fma / float-pass sequence run on the device (GEMMUL8_B200_ENCODE=reference), all magnitudes."""
+    rint / fma / float-pass sequence run on the device (option encode_reference), all magnitudes."""
     torch = torch_()
     for (m, n, k, N, dt, phi) in [(300, 200, 700, 14, "float64", 0.5), (300, 200, 700, 20, "float64", 4.0),
                                   (300, 200, 700, 6, "float32", 0.5), (300, 200, 700, 19, "float32", 1.5)]:
         A, B = operands(g, m, n, k, 0, 0, getattr(torch, dt), getattr(torch, dt), phi=phi, seedB=31)
-        monkeypatch.delenv("GEMMUL8_B200_ENCODE", raising=False)
+        g.set_option("encode_reference", 0)
         _, v = run_ours(g, m, n, k, N, True, A, B, flags=g.FLAG_STAGE_SCALING)
-        monkeypatch.setenv("GEMMUL8_B200_ENCODE", "reference")
+        g.set_option("encode_reference", 1)
         _, w = run_ours(g, m, n, k, N, True, A, B, flags=g.FLAG_STAGE_SCALING)
-        monkeypatch.delenv("GEMMUL8_B200_ENCODE", raising=False)
+        g.set_option("encode_reference", 0)
         assert torch.equal(v["A8i"][:, :m], w["A8i"][:, :m]) and torch.equal(v["B8i"], w["B8i"])
 
 
@@ -268,14 +268,14 @@ def test_two_call_split_equals_single_call(g):
 
 
 def test_cta_pair_kernel(g, monkeypatch):
-    """The opt-in cta_group::2 kernel (two CTAs share a 256 x 256 tile, OZ_GEMM_PAIR=1): bit-identical residues and C,
+    """The opt-in cta_group::2 kernel (two CTAs share a 256 x 256 tile, option gemm_pair = 1): bit-identical residues and C,
     ragged shapes included, and through the complex combine passes."""
     torch = torch_()
     for (m, n, k, N) in [(777, 1301, 900, 14), (300, 200, 4096, 8), (129, 257, 130, 20)]:
         A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=5)
-        monkeypatch.setenv("OZ_GEMM_PAIR", "0")
+        g.set_option("gemm_pair", 0)
         C, v = run_ours(g, m, n, k, N, True, A, B)
-        monkeypatch.setenv("OZ_GEMM_PAIR", "1")
+        g.set_option("gemm_pair", 1)
         Cp, vp = run_ours(g, m, n, k, N, True, A, B)
         assert torch.equal(v["C8u"][:, :, :m], vp["C8u"][:, :, :m]) and torch.equal(C, Cp)
     m, n, k, N = 333, 222, 444, 13
@@ -283,13 +283,13 @@ def test_cta_pair_kernel(g, monkeypatch):
     Bz = g.phi_matrix(k, n, 0.5, torch.complex128, seed=2)
     outs = []
     for pair in ("0", "1"):
-        monkeypatch.setenv("OZ_GEMM_PAIR", pair)
+        g.set_option("gemm_pair", int(pair))
         Cz = torch.zeros((n, m), dtype=torch.complex128, device="cuda")
         work = torch.zeros(g.workSize(m, n, k, N, g.COMPLEX_KARATSUBA_MULT), dtype=torch.uint8, device="cuda")
         g.gemm(None, 0, 0, m, n, k, 1.0, Az, m, Bz, k, 0.0, Cz, m, N, True, work, computeType=g.COMPLEX_KARATSUBA_MULT)
         torch.cuda.synchronize()
         outs.append(Cz)
-    monkeypatch.delenv("OZ_GEMM_PAIR", raising=False)
+    g.set_option("gemm_pair", -1)
     assert torch.equal(torch.view_as_real(outs[0]), torch.view_as_real(outs[1]))
 
 

@@ -28,6 +28,6 @@ real(77, 45, 33, 6, True, 0, 1, torch.float32)
 for ct in (1, 2, 3):
     cplx(130, 70, 101, 9, True, 0, 2, torch.complex128, ct)
     cplx(70, 52, 100, 8, False, 1, 0, torch.complex64, ct)
-os.environ["OZ_GEMM_PAIR"] = "1"
+g.set_option("gemm_pair", 1)
 real(300, 520, 260, 14, True, 0, 0, torch.float64)
 print("sanitize workload done")
