@@ -11,14 +11,19 @@ N > 1 : one rank per GPU (torchrun), 2-D block decomposition of C (P x Q grid), 
         rank owns a 16384 x 16384 block of C with k = 16384; A row panels / B column panels are
         assembled with NCCL all-gathers inside the timed region.  value = total flops / max-rank time.
 --impl reference : the UNMODIFIED reference library (oracle/_ref/libgemmul8_ref.so: its own
-        kernels + cuBLAS int8 GEMM) on the same GPU and config.  The reference's API only takes device
-        pointers, so its `value` is measured like our `e2e`: pinned host buffers, copies in the timed
-        region (a caller holding host data pays them with either library); its device-resident
-        number is reported as `device_resident`.
+        kernels + cuBLAS int8 GEMM) on the same GPU, the same inputs and the same `config`, measured
+        the same way: `value` = device-resident calls, `e2e` = pinned host A, B in and C out around
+        the call (the reference's API takes device pointers only, so a caller holding host data makes
+        these copies itself).
 
-The line also carries `roofline` (the tcgen05 GEMM kernel against the int8 tensor peak = 2 x the
-measured bf16 figure of MEASURED_PEAKS.json), `cpu_baseline` (the reference's host GEMM,
-double-double, restated in oracle/oracle.c, on this box's cores at 1024^3), `accuracy`, `clocks`.
+Both arms build their inputs with torch's generator (same seeds): nothing of this repository is
+loaded by the reference arm except the ctypes door to the reference library (oracle/oracle.py).
+The line also carries `roofline` (the tcgen05 GEMM kernel against the int8 tensor peak MEASURED IN
+THIS RUN: cuBLASLt int8 16384^3 on random data through torch._int_mm, burst and sustained; 2 x the
+bf16 figure of MEASURED_PEAKS.json is reported beside it), `cpu_baseline` (the reference's host GEMM,
+double-double, restated in oracle/oracle.c, on this box's cores at 1024^3), `accuracy`, `clocks`;
+N > 1 adds `parity` (tools/dist_check.py's three comparisons, outside the timed region) and, where the
+problem fits, `config5` (BASELINE config 5: ONE 65536^3 product block-partitioned over the grid).
 """
 import argparse
 import json
@@ -49,6 +54,8 @@ def parse():
     ap.add_argument("--accurate", action="store_true", help="accurate mode instead of fast mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 65536^3 sub-record (N = 1: low-memory call; N >= 4: --strong)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity checks after the timed region")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: ONE m = n = k = --size problem block-partitioned over the P x Q grid (BASELINE config 5: --size 65536) "
                          "instead of the default weak scaling (one --size^2 block of C per GPU)")
@@ -112,20 +119,85 @@ def peaks():
 
 
 def ncu_traffic(m_loc, n_loc, k, N):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/r01_ncu_full_v3_raw.csv, one launch at 16384^3, 14 moduli); null for other per-GPU shapes."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the most recent committed
+    `ncu --set full` capture of this shape (profiles/r*_ncu_traffic.json, written by tools/ncu_traffic.py; a run cannot
+    read DRAM counters itself); null for other per-GPU shapes.  Returns (bytes, file)."""
     if (m_loc, n_loc, k, N) != (16384, 16384, 16384, 14):
-        return None
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    try:
-        return json.load(open(path))[dominant_kernel()]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+        return None, None
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+        try:
+            return json.load(open(path))[dominant_kernel()]["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 def dominant_kernel():
     """The all-moduli GEMM the library launches by default: the CTA-pair kernel unless OZ_GEMM_PAIR=0."""
     return "oz_gemm_tcgen05_kernel" if os.environ.get("OZ_GEMM_PAIR", "") == "0" else "oz_gemm_pair_kernel"
+
+
+def phi_torch(torch, rows, cols, phi, seed):
+    """(U - 0.5) * exp(phi * Z), the reference's synthetic input (GEMMul8/testing/make_matrix.hpp:14-21) drawn from torch's
+    generator: column-major rows x cols as a (cols, rows) tensor.  Both bench arms call this with the same seeds."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    out = torch.rand((cols, rows), dtype=torch.float64, device="cuda", generator=gen).sub_(0.5)
+    z = torch.randn((cols, rows), dtype=torch.float64, device="cuda", generator=gen).mul_(phi).exp_()
+    return out.mul_(z)
+
+
+def int8_peak(torch, seconds=2.0, S=16384):
+    """Dense int8 tensor peak of THIS GPU, measured here: cuBLASLt s8 x s8 -> s32 (torch._int_mm), S^3, random int8 data
+    (the reference driver's "INT8-GEMM" row, GEMMul8/testing/test_double.cu:287-309, uses all-ones data, which draws less
+    power and clocks higher).  Returns TOP/s: best single call (burst) and a back-to-back loop of >= `seconds` (sustained)."""
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        a = torch.randint(-127, 128, (S, S), dtype=torch.int8, device="cuda", generator=gen)
+        bt = torch.randint(-127, 128, (S, S), dtype=torch.int8, device="cuda", generator=gen)
+        b = bt.t()                                     # column-major B: the TN layout cuBLASLt's int8 kernels take
+        ops = 2.0 * S ** 3
+        for _ in range(3):
+            c = torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            c = torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sust = e0.elapsed_time(e1) / reps
+        del a, bt, b, c
+        # the reference driver's own "INT8-GEMM" row: 8192^3, all-ones data (low toggle rate: less power, higher clock)
+        S1 = 8192
+        one = torch.ones((S1, S1), dtype=torch.int8, device="cuda")
+        for _ in range(3):
+            c = torch._int_mm(one, one.t())
+        torch.cuda.synchronize()
+        best1 = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = torch._int_mm(one, one.t())
+            e1.record()
+            torch.cuda.synchronize()
+            best1 = min(best1, e0.elapsed_time(e1))
+        del one, c
+        return {"burst": ops / (best * 1e-3) / 1e12, "sustained": ops / (sust * 1e-3) / 1e12, "unit": "TOP/s",
+                "all_ones_8192_burst": 2.0 * S1 ** 3 / (best1 * 1e-3) / 1e12,
+                "how": f"torch._int_mm (cuBLASLt s8s8s32) {S}^3 random int8, best of 10 / {reps} calls back to back ({sust * reps / 1e3:.1f} s); "
+                       "all_ones_8192_burst = the reference driver's INT8-GEMM row (GEMMul8/testing/test_double.cu:287-309), best of 10"}
+    except Exception as e:     # no int8 path in this torch build: the caller falls back to 2 x bf16
+        return {"error": str(e)[:200]}
 
 
 def cpu_baseline(sample=1024):
@@ -158,6 +230,29 @@ def accuracy_sample(g, torch, m, n, k, A, B, Cm, nsamp=256):
             "sample": f"{rows.numel()}x{cols.numel()} elements of C vs double-double truth"}
 
 
+def workload_text(m, n, k, N, fast):
+    return f"DGEMM emulation m={m} n={n} k={k}, {N} moduli, {'fast' if fast else 'accurate'} mode, phi={PHI}, ops N/N, alpha=1 beta=0"
+
+
+def config_of(m, n, k, N, fast, world, grid_text=""):
+    """The `config` object: identical keys and, for the same workload, identical values in both arms."""
+    return {"workload": workload_text(m, n, k, N, fast),
+            "parallelism": f"{world} GPU(s)" + grid_text,
+            "l2": f"inputs ({8 * (m * k + k * n) / world / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no explicit flush"}
+
+
+def timed_loop(torch, step, steps, barrier, flag=0):
+    """EXACTLY `steps` asynchronous calls between two events, barrier + synchronize on both sides."""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step(flag)
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -168,16 +263,10 @@ def main():
         return 0  # the reference is single-GPU: rank 0 alone runs and prints
 
     import torch
-    import gemmul8_b200 as g
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for this path)")
     torch.cuda.set_device(local_rank)
-    multi = world > 1 and args.impl == "ours"
-    if multi:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    bf16_burst, bf16_sust, hbm, peak_src = peaks()
     N, fast = args.moduli, not args.accurate
     S = args.size
     sampler = ClockSampler(local_rank)
@@ -187,30 +276,58 @@ def main():
            "dtype": "int8 (s8 x s8 -> s32 tensor cores) + f64 CRT", "data": "synthetic"}
 
     if args.impl == "reference":
-        return reference_arm(args, torch, g, out, sampler)
+        return reference_arm(args, torch, out, sampler)
 
+    import gemmul8_b200 as g
+    multi = world > 1
+    if multi:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g.init()                                  # placement probe + tuning defaults: outside every timed region
+    bf16_burst, bf16_sust, hbm, peak_src = peaks()
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if not multi:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    grid = None
     if multi:
         from importlib import import_module
         dmod = import_module("gemmul8_b200.distributed")
         grid = dmod.BlockGrid()
-        m, n, k = (S, S, S) if args.strong else (S * grid.P, S * grid.Q, S)
+
+    def multi_problem(m, n, k):
+        """Operands and the step of one partitioned problem: every rank generates only the pieces it owns."""
         m_loc, n_loc = grid.block_dims(m, n)
         klo, khi = grid.a_slice_k(k)
         clo, chi = grid.b_slice_cols(n_loc)
-        # every rank generates only the pieces it owns (distinct seeds per piece keep it cheap and deterministic)
-        a_slice = g.phi_matrix(m_loc, khi - klo, PHI, torch.float64, seed=SEED + 17 * rank)
-        b_slice = g.phi_matrix(k, chi - clo, PHI, torch.float64, seed=SEED + 17 * rank + 7)
-        ws = g.workSize(m_loc, n_loc, k, N)
-        work = torch.empty(ws, dtype=torch.uint8, device="cuda")
+        a_slice = phi_torch(torch, m_loc, khi - klo, PHI, SEED + 17 * rank)
+        b_slice = phi_torch(torch, k, chi - clo, PHI, SEED + 17 * rank + 7)
+        work = torch.empty(g.workSize(m_loc, n_loc, k, N), dtype=torch.uint8, device="cuda")
         Cm = torch.zeros((n_loc, m_loc), dtype=torch.float64, device="cuda")
 
         def step(flags=0):
             return dmod.pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, Cm, N, fast, work, flags=flags)
+        return step, m_loc, n_loc, (a_slice, b_slice, work, Cm)
+
+    if multi:
+        m, n, k = (S, S, S) if args.strong else (S * grid.P, S * grid.Q, S)
+        step, m_loc, n_loc, keep = multi_problem(m, n, k)
+        Cm = keep[3]
     else:
         m = n = k = S
-        A = g.phi_matrix(m, k, PHI, torch.float64, seed=SEED)
-        # the reference drivers use the same seed for B, so for a square problem B's array equals A's
-        B = A if (args.lowmem and 3 * 8 * S * S > 120e9) else g.phi_matrix(k, n, PHI, torch.float64, seed=SEED)
+        m_loc, n_loc = m, n
+        A = phi_torch(torch, m, k, PHI, SEED)
+        # at 65536 the three fp64 matrices alone are 103 GB: B shares A's array there (the reference drivers also draw B from A's seed)
+        B = A if (args.lowmem and 3 * 8 * S * S > 120e9) else phi_torch(torch, k, n, PHI, SEED + 1)
         Cm = torch.zeros((n, m), dtype=torch.float64, device="cuda")
         if args.lowmem:
             free = torch.cuda.mem_get_info()[0] - (2 << 30)
@@ -227,32 +344,20 @@ def main():
             def step(flags=0):
                 return g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, Cm, m, N, fast, work, flags=flags)
 
-    def barrier():
-        if multi:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     sampler.start()       # nvidia-smi needs a moment to come up: start it before the warm-up so the timed region is covered
     big = S > 32768                      # seconds per step: fewer warm-up and instrumented calls
     for _ in range(args.warmup if big else max(args.warmup, 3)):
         step()
     barrier()
     launches0 = g.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
     live_phases = not args.lowmem and fast
     if live_phases:
         g.phase_log_collect()       # empty the log
-    for _ in range(args.steps):
-        step(g.FLAG_PHASE_LOG if live_phases else 0)   # asynchronous calls; the only instrumentation is 4 event records per call
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    # asynchronous calls; the only instrumentation is 4 event records per call (FLAG_PHASE_LOG: no host wait anywhere)
+    ms = timed_loop(torch, step, args.steps, barrier, g.FLAG_PHASE_LOG if live_phases else 0)
     clocks = sampler.stop()
     launches = g.launch_count() - launches0
     if live_phases:
-        # phase boundaries were recorded as events INSIDE the timed region (FLAG_PHASE_LOG: no host wait anywhere)
         phase, psteps = g.phase_log_collect()
         phase_how = "CUDA events recorded on the launching stream inside the timed region, no synchronisation between or after the calls"
     else:
@@ -266,44 +371,23 @@ def main():
     if multi and live_phases:
         # scale / product steps of the pipelined exchange are logged one by one: bring the counts back to "per step"
         psteps = args.steps
+    ms = allmax(ms)
     if multi:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = tt.item()
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt)
         launches = int(lt.item())
     ms_step = ms / args.steps
     flops = 2.0 * m * n * k
     out.update({"value": flops / (ms_step * 1e-3) / 1e12, "ms_per_step": ms_step, "gpu_launches": launches, "clocks": clocks})
-
-    # roofline of the dominant kernel (the all-moduli tcgen05 GEMM), from the live per-phase events
     gemm_ms = phase[1] / psteps / 1e6
-    per_gpu_ops = 2.0 * N * (m * n * k / world)
-    long_step = gemm_ms > 20.0
-    peak = 2.0 * (bf16_sust if long_step else bf16_burst)
-    ach = per_gpu_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                       "traffic": ncu_traffic(m_loc if multi else m, n_loc if multi else n, k, N), "kernel": dominant_kernel() + " (all moduli in one launch, residue reduction in the epilogue)", "kernel_ms": gemm_ms,
-                       "peak_source": f"2 x bf16 {'sustained' if long_step else 'burst'} of {peak_src}: kind::i8 issues at twice the bf16 rate; "
-                                      "kernel_ms: " + phase_how,
-                       "algorithmic_ops": "2*N*m*n*k int8 ops per launch"}
-    ml, nl = (m_loc, n_loc) if multi else (m, n)
-    enc_bytes = (8.0 * 2 + N) * (ml * k + k * nl)   # per GPU: two passes over its fp64 panels + their int8 slices out
     scal_ms = phase[0] / psteps / 1e6
-    out["phases_ms"] = {"scaling": scal_ms, "int8_gemm_fused_residue": gemm_ms, "crt_inverse_scaling": phase[3] / psteps / 1e6,
-                        "scaling_GBps": enc_bytes / (scal_ms * 1e-3) / 1e9 if scal_ms > 0 else None, "hbm_peak_GBps": hbm}
-    if multi and live_phases:
-        out["phases_ms"]["exposed_exchange_and_gaps"] = ms_step - (scal_ms + gemm_ms + phase[3] / psteps / 1e6)
-        out["phases_ms"]["note"] = "rank 0; kernels timed by events inside the timed region, the rest of the step is waiting for panel pieces"
-    out["config"] = {"workload": f"DGEMM emulation m={m} n={n} k={k}, {N} moduli, {'fast' if fast else 'accurate'} mode, phi={PHI}, ops N/N, alpha=1 beta=0",
-                     "parallelism": f"{world} GPU(s)" + (f", {grid.P}x{grid.Q} C-block grid, NCCL all-gather of FP64 panels" if multi else ""),
-                     "l2": f"inputs ({8 * (m * k + k * n) / world / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no explicit flush"}
+    crt_ms = phase[3] / psteps / 1e6
+    grid_text = f", {grid.P}x{grid.Q} C-block grid, NCCL all-gather of FP64 panels" if multi else ""
+    out["config"] = config_of(m, n, k, N, fast, world, grid_text)
 
-    if rank == 0 and not multi and big:
+    if rank == 0 and not multi:
         out["accuracy"] = accuracy_sample(g, torch, m, n, k, A, B, Cm)
-    elif rank == 0 and not multi:
-        out["accuracy"] = accuracy_sample(g, torch, m, n, k, A, B, Cm)
+    if rank == 0 and not multi and not big:
         # native cuBLAS DGEMM on the same inputs, for the "beats native DGEMM" target
         Cn = torch.empty((n, m), dtype=torch.float64, device="cuda")
         for _ in range(2):
@@ -318,8 +402,8 @@ def main():
         del Cn
 
     # ---- the north-star target: beat native DGEMM at an accuracy at least equal to native DGEMM's ----
-    # (14 moduli in fast mode are slightly less accurate than native DGEMM on this input; 15 are more accurate)
-    if rank == 0 and not multi and not big and N == 14 and fast and "native_dgemm_tflops" in out:
+    # (14 moduli in fast mode are slightly less accurate than native DGEMM on this input; 15 or 16 are more accurate)
+    if rank == 0 and not multi and not big and not args.lowmem and N == 14 and fast and "native_dgemm_tflops" in out:
         for N2 in (15, 16, 17):
             work2 = torch.empty(g.workSize(m, n, k, N2), dtype=torch.uint8, device="cuda")
             for _ in range(2):
@@ -361,7 +445,8 @@ def main():
         out["e2e"] = {"value": flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": 8 * (m * k + k * n),
                       "d2h_bytes_per_step": 8 * m * n, "ms_per_step": e2e_ms, "steps": ksteps,
                       "api": "gemmul8_b200_gemm_host (pinned host A, B, C; 8 x 8 block wavefront: H2D, compute and D2H overlap)",
-                      "checksum": float(hC[::97, ::89].sum())}
+                      "checksum": float(hC[::97, ::89].sum()),
+                      "equals_device_resident_result": bool(torch.equal(hC, Cm.cpu()))}
         # the same call with the copies in series (what a caller of the reference does around its gemm)
         e0.record()
         for _ in range(2):
@@ -369,8 +454,110 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         out["e2e"]["serial_copies_ms_per_step"] = e0.elapsed_time(e1) / 2
+        del hA, hB, hC, scratch
     else:
         out["e2e"] = None
+
+    # ---- roofline of the dominant kernel (the all-moduli tcgen05 GEMM), from the live per-phase events, against the
+    #      int8 peak measured here (after the timed regions, so that it cannot disturb them) ----
+    i8 = int8_peak(torch) if (rank == 0 or multi) and not big else {"error": "skipped"}
+    per_gpu_ops = 2.0 * N * (m * n * k / world)
+    long_step = gemm_ms > 20.0
+    bf16x2 = 2.0 * (bf16_sust if long_step else bf16_burst)
+    kind = "sustained" if long_step else "burst"
+    if "error" not in i8:
+        # the denominator is the HIGHER of the two measured figures (cuBLASLt's int8 kernels sustain less than twice its bf16 rate
+        # on this part, so taking the int8 number alone would flatter the kernel)
+        peak = max(i8[kind], bf16x2)
+        peak_source = (f"max of two measured {kind} figures: cuBLASLt int8 in this run = {i8[kind]:.0f} ({i8['how']}) and 2 x bf16 {kind} of "
+                       f"{peak_src} = {bf16x2:.0f} (kind::i8 issues at twice the bf16 rate)")
+    else:
+        peak = bf16x2
+        peak_source = f"2 x bf16 {kind} of {peak_src} (no int8 cuBLASLt path in this torch: {i8['error']})"
+    ach = per_gpu_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic, traffic_file = ncu_traffic(m_loc, n_loc, k, N)
+    out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                       "traffic": traffic, "traffic_source": traffic_file,
+                       "kernel": dominant_kernel() + " (all moduli in one launch, residue reduction in the epilogue)", "kernel_ms": gemm_ms,
+                       "peak_source": peak_source + "; kernel_ms: " + phase_how,
+                       "int8_peak_measured": i8, "frac_of_2x_bf16": ach / bf16x2 if bf16x2 else None,
+                       "frac_of_int8_measured": (ach / i8[kind]) if "error" not in i8 else None,
+                       "frac_of_int8_all_ones_burst": (ach / i8["all_ones_8192_burst"]) if "error" not in i8 else None,
+                       "algorithmic_ops": "2*N*m*n*k int8 ops per launch"}
+    enc_bytes = (8.0 + N) * (m_loc * k + k * n_loc)   # per GPU, ALGORITHMIC: its fp64 panels in once + their int8 slices out
+    out["phases_ms"] = {"scaling": scal_ms, "int8_gemm_fused_residue": gemm_ms, "crt_inverse_scaling": crt_ms,
+                        "scaling_GBps_algorithmic": enc_bytes / (scal_ms * 1e-3) / 1e9 if scal_ms > 0 else None,
+                        "crt_GBps_algorithmic": 8.0 * m_loc * n_loc / (crt_ms * 1e-3) / 1e9 if crt_ms > 0 else None, "hbm_peak_GBps": hbm}
+    if multi and live_phases:
+        out["phases_ms"]["exposed_exchange_and_gaps"] = ms_step - (scal_ms + gemm_ms + crt_ms)
+        out["phases_ms"]["note"] = "rank 0; kernels timed by events inside the timed region, the rest of the step is waiting for panel pieces"
+
+    # ---- N > 1: parity of the partitioned path (outside the timed region), then BASELINE config 5 ----
+    if multi and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import dist_check
+        try:
+            # the block of C the timed steps left behind, against a double-double product of the gathered panels
+            a_panel = grid.gather_a_panel(keep[0], m_loc, k)
+            b_panel = grid.gather_b_panel(keep[1], n_loc, k)
+            rows = torch.arange(0, m_loc, max(1, m_loc // 64), dtype=torch.int32, device="cuda")
+            cols = torch.arange(0, n_loc, max(1, n_loc // 64), dtype=torch.int32, device="cuda")
+            T1, T2 = g.dd_gemm(m_loc, n_loc, k, a_panel, m_loc, b_panel, k, rows=rows, cols=cols)
+            err = allmax((((Cm[cols.long()][:, rows.long()] - T1) - T2) / T1).abs().max().item())
+            del a_panel, b_panel, T1, T2
+            par = dist_check.run_checks(grid, dmod, 1024, verbose=False)
+            par["timed_result_relerr_max_vs_dd"] = err
+            par["ok"] = bool(par["ok"] and err < (1e-6 if N >= 14 else 1e-2))
+            par["what"] = ("tools/dist_check.run_checks on every rank: pipelined exchange == plain exchange bit for bit, sampled double-double "
+                           "truth, accurate-mode block == block of the unpartitioned accurate product bit for bit; plus the timed run's own C "
+                           "block against a sampled double-double truth (max over ranks)")
+        except Exception as e:
+            par = {"ok": False, "error": str(e)[:300]}
+        out["parity"] = par
+    if multi and not args.no_config5 and not args.strong and world >= 4 and N == 14 and fast:
+        del keep, Cm, step
+        torch.cuda.empty_cache()
+        try:
+            S5 = 65536
+            step5, m5, n5, keep5 = multi_problem(S5, S5, S5)
+            step5()
+            barrier()
+            g.phase_log_collect()
+            ms5 = allmax(timed_loop(torch, step5, 2, barrier, g.FLAG_PHASE_LOG)) / 2
+            ph5, _ = g.phase_log_collect()
+            out["config5"] = {"workload": workload_text(S5, S5, S5, N, fast), "scaling": "strong", "n_gpus": world, "grid": f"{grid.P}x{grid.Q}",
+                              "steps": 2, "warmup": 1, "ms_per_step": ms5, "value": 2.0 * S5 ** 3 / (ms5 * 1e-3) / 1e12, "unit": "TFLOPS",
+                              "phases_ms_rank0": {"scaling": ph5[0] / 2e6, "int8_gemm_fused_residue": ph5[1] / 2e6, "crt_inverse_scaling": ph5[3] / 2e6},
+                              "note": "BASELINE config 5; parallel efficiency = (1-GPU config5.ms_per_step of the N=1 line) / (n_gpus * this ms_per_step)"}
+            del keep5, step5
+        except Exception as e:
+            out["config5"] = {"error": str(e)[:300]}
+    if not multi and not args.no_config5 and not args.lowmem and not big and N == 14 and fast and S == 16384:
+        # BASELINE config 5 on ONE GPU (its workSize() is 184 GiB: the low-memory call with a 64 GiB workspace): the denominator
+        # of the multi-GPU efficiency, measured by the same driver run
+        try:
+            del A, B, Cm, work, step
+            torch.cuda.empty_cache()
+            S5 = 65536
+            A5 = phi_torch(torch, S5, S5, PHI, SEED)
+            C5 = torch.zeros((S5, S5), dtype=torch.float64, device="cuda")
+            free = torch.cuda.mem_get_info()[0] - (3 << 30)
+            mb, nb, ws5 = g.plan_blocks(S5, S5, S5, N, min(64 << 30, free))
+            work5 = torch.empty(ws5, dtype=torch.uint8, device="cuda")
+
+            def step5(flags=0):
+                return g.gemm_blocked(None, 0, 0, S5, S5, S5, 1.0, A5, S5, A5, S5, 0.0, C5, S5, N, True, work5, mb, nb, flags=flags)
+            step5()
+            ms5 = timed_loop(torch, step5, 1, barrier)
+            acc5 = accuracy_sample(g, torch, S5, S5, S5, A5, A5, C5, nsamp=64)
+            out["config5"] = {"workload": workload_text(S5, S5, S5, N, fast), "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": ms5,
+                              "value": 2.0 * S5 ** 3 / (ms5 * 1e-3) / 1e12, "unit": "TFLOPS",
+                              "api": f"gemmul8_b200_gemm_blocked, blocks {mb} x {nb}, workspace {ws5 / 2 ** 30:.1f} GiB (workSize() = {g.workSize(S5, S5, S5, N) / 2 ** 30:.0f} GiB); B shares A's array",
+                              "relerr_max": acc5["relerr_max"]}
+            del A5, C5, work5
+        except Exception as e:
+            out["config5"] = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         if not args.no_cpu_baseline and not multi:
@@ -385,15 +572,15 @@ def main():
     return 0
 
 
-def reference_arm(args, torch, g, out, sampler):
+def reference_arm(args, torch, out, sampler):
     import oracle
     if not oracle.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgemmul8_ref.so not built (needs /root/reference at build time)"}))
         return 0
     N, fast, S = args.moduli, not args.accurate, args.size
     m = n = k = S
-    A = g.phi_matrix(m, k, PHI, torch.float64, seed=SEED)
-    B = g.phi_matrix(k, n, PHI, torch.float64, seed=SEED)
+    A = phi_torch(torch, m, k, PHI, SEED)
+    B = phi_torch(torch, k, n, PHI, SEED + 1)
     ws = oracle.ref_worksize(m, n, k, N)
     work = torch.empty(ws, dtype=torch.uint8, device="cuda")
     Cm = torch.zeros((n, m), dtype=torch.float64, device="cuda")
@@ -413,10 +600,11 @@ def reference_arm(args, torch, g, out, sampler):
         torch.cuda.synchronize()
         return t
 
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_dev()
     torch.cuda.synchronize()
-    # device-resident number (reported, not the headline)
+    # `value`: device-resident, exactly like our arm's `value`
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ph = [0.0] * 4
     e0.record()
@@ -425,32 +613,30 @@ def reference_arm(args, torch, g, out, sampler):
     e1.record()
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1) / args.steps
-    # host-buffer number: what a caller with host data pays with the reference
+    clocks = sampler.stop()
+    # `e2e`: pinned host buffers, copies inside the timed region, exactly like our arm's `e2e`
     step_host()
-    sampler.start()
+    ksteps = max(3, min(args.steps, 5))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(ksteps):
         step_host()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop()
-    val = flops / (ms * 1e-3) / 1e12
-    out.update({"impl": "reference", "value": val, "ms_per_step": ms, "clocks": clocks,
-                "e2e": {"value": val, "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                        "note": "the reference takes device pointers only; this arm times pinned-host copies of A, B in and C out "
-                                f"around its gemm ({8 * (m * k + k * n)} B in, {8 * m * n} B out per step), like our e2e"},
-                "device_resident": {"value": flops / (dev_ms * 1e-3) / 1e12, "unit": "TFLOPS", "ms_per_step": dev_ms,
-                                    "phases_ms": {"scaling": ph[0] / args.steps / 1e6, "cublas_int8_gemm": ph[1] / args.steps / 1e6,
-                                                  "int32_to_uint8": ph[2] / args.steps / 1e6, "inverse_scaling": ph[3] / args.steps / 1e6}},
-                "config": {"workload": f"DGEMM emulation m={m} n={n} k={k}, {N} moduli, {'fast' if fast else 'accurate'} mode, phi={PHI}, ops N/N, alpha=1 beta=0",
-                           "library": "unmodified ptrkgtsch/mixed-GEMMul8 (sm_100 build, cuBLAS int8 GEMM)"},
+    ms = e0.elapsed_time(e1) / ksteps
+    out.update({"impl": "reference", "value": flops / (dev_ms * 1e-3) / 1e12, "ms_per_step": dev_ms, "clocks": clocks,
+                "e2e": {"value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": 8 * (m * k + k * n),
+                        "d2h_bytes_per_step": 8 * m * n, "ms_per_step": ms, "steps": ksteps,
+                        "api": "the reference takes device pointers only: pinned-host copies of A, B in and C out around its gemm, in series",
+                        "checksum": float(hC[::97, ::89].sum())},
+                "phases_ms": {"scaling": ph[0] / args.steps / 1e6, "cublas_int8_gemm": ph[1] / args.steps / 1e6,
+                              "int32_to_uint8": ph[2] / args.steps / 1e6, "inverse_scaling": ph[3] / args.steps / 1e6},
+                "config": config_of(m, n, k, N, fast, 1),
+                "reference_library": "unmodified ptrkgtsch/mixed-GEMMul8 (sm_100 build of its own sources, cuBLAS int8 GEMM), oracle/_ref/libgemmul8_ref.so",
                 "gpu_launches": 0})
     if not args.no_cpu_baseline:
         try:
-            cb = cpu_baseline()
-            out["cpu_baseline"] = cb
+            out["cpu_baseline"] = cpu_baseline()
         except Exception as e:
             out["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(out), flush=True)

@@ -43,7 +43,7 @@ def _run(cmd):
 
 def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gemmul8_b200.h"), os.path.join(HERE, "..", "include", "gemmul8.hpp")]
-    core = [os.path.join(CSRC, f) for f in ("oz_api.cu", "oz_scale.cu", "oz_gemm.cu", "oz_crt.cu", "oz_complex.cu", "oz_cxx_api.cu")
+    core = [os.path.join(CSRC, f) for f in ("oz_api.cu", "oz_scale.cu", "oz_gemm.cu", "oz_gemm_crt.cu", "oz_crt.cu", "oz_complex.cu", "oz_cxx_api.cu")
             if os.path.exists(os.path.join(CSRC, f))]
     out = ""
     if force or _stale(LIB, deps):

@@ -227,6 +227,36 @@ int scale_operand(int dtype, bool strided, const void *X, size_t ld, size_t nvec
     return GEMMUL8_OK;
 }
 
+// Which product path a real-type block takes: the single kernel (product + residues + CRT, oz_gemm_crt.cu) when the caller
+// forces it (GEMMUL8_FLAG_FUSED_CRT) or k is at most the option "fused_k"; product + residues to HBM and the stand-alone
+// CRT kernel otherwise.  Both give the same bits of C.
+bool take_fused(const gemmul8_b200_args *a) {
+    if (a->flags & (GEMMUL8_FLAG_GEMM_SIMT | GEMMUL8_FLAG_STAGE_RESIDUES | GEMMUL8_FLAG_STAGE_SCALING)) return false;
+    if (a->flags & GEMMUL8_FLAG_FUSED_CRT) return true;
+    const int fk = oz::tuning().fused_k;
+    return fk > 0 && a->k <= (size_t)fk;
+}
+// product of the block described by gp (A8i / B8i / rows / C8u set by the caller) into C: marks the timer between the
+// product and the CRT when they are separate kernels
+int block_to_c(const gemmul8_b200_args *a, oz::GemmProblem &gp, bool fused, bool split, void *C, const int16_t *sftA, const int16_t *sftB,
+               cudaStream_t st, PhaseTimer *timer) {
+    if (fused) {
+        gp.C = C; gp.ldc = a->ldc; gp.dtype_C = a->dtype_C; gp.split_weights = split; gp.sftA = sftA; gp.sftB = sftB;
+        gp.alpha_ptr = a->alpha; gp.beta_ptr = a->beta; gp.device_scalars = dev_scalars(a);
+        OZ_CUDA(oz::launch_gemm_crt(gp, st), "int8 gemm + crt");
+        if (timer) timer->mark();
+        return GEMMUL8_OK;
+    }
+    auto gemm = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
+    OZ_CUDA(gemm(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+    if (timer) timer->mark();
+    if (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) return GEMMUL8_OK;
+    OZ_CUDA(oz::launch_crt(a->dtype_C, split, gp.num_slices, gp.rowsA, gp.rowsB, gp.C8u, gp.ldc8u, gp.sizeC, C, a->ldc, sftA, sftB, a->alpha, a->beta,
+                           dev_scalars(a), st), "crt");
+    if (timer) timer->mark();
+    return GEMMUL8_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Column-strip pipeline of the device-resident real fast-mode call.  The three phases of a strip
 // use different units (encode: FP64 + LSU, product: tensor, CRT: FP64 + LSU), so on three streams
@@ -400,26 +430,8 @@ int gemm_real(gemmul8_b200_args *a) {
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.B8i = B8i; gp.rowsA = m; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
     gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
-    // Default: item-major GEMM + the stand-alone CRT kernel.  The single-kernel variant (every CTA walks all
-    // moduli of its tile, CRT warps behind the last modulus) is kept behind GEMMUL8_FLAG_FUSED_CRT: on
-    // B200 its tile-major schedule costs more L2 misses than the CRT pass saves ("What was tried").
-    const bool staged = simt || (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) != 0 || (a->flags & GEMMUL8_FLAG_FUSED_CRT) == 0;
-    if (!staged) {
-        gp.C = a->C; gp.ldc = a->ldc; gp.dtype_C = a->dtype_C; gp.split_weights = split; gp.sftA = sftA; gp.sftB = sftB;
-        if (a->dtype_C == GEMMUL8_F64) { gp.alpha = *static_cast<const double *>(a->alpha); gp.beta = *static_cast<const double *>(a->beta); }
-        else                           { gp.alpha = *static_cast<const float *>(a->alpha);  gp.beta = *static_cast<const float *>(a->beta); }
-        OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_CRT, st), "int8 gemm + crt");
-        timer.mark();
-        timer.finish(a->timers_ns);
-        return GEMMUL8_OK;
-    }
-    OZ_CUDA(gemm(gp, oz::EPI_RESIDUE, st), "int8 gemm");
-    timer.mark();
-    if (a->flags & GEMMUL8_FLAG_STAGE_RESIDUES) { timer.finish(a->timers_ns); return GEMMUL8_OK; }
-
-    // ---------------- phase 3: CRT + inverse scaling ----------------
-    OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, n, C8u, L.m_pad, L.sizeC, a->C, a->ldc, sftA, sftB, a->alpha, a->beta, dev_scalars(a), st), "crt");
-    timer.mark();
+    int rc = block_to_c(a, gp, take_fused(a), split, a->C, sftA, sftB, st, &timer);
+    if (rc) return rc;
     timer.finish(a->timers_ns);
     return GEMMUL8_OK;
 }
@@ -632,11 +644,10 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
         gp.C8u = C8u + col0 * L.m_pad + row0;
         gp.share_sm = true;   // a block-wise caller overlaps this product with transfers of the next pieces
         timer.mark();
-        OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
-        timer.mark();
-        OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, row1 - row0, col1 - col0, gp.C8u, L.m_pad, L.sizeC,
-                               static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, a->ldc, sftA + row0, sftB + col0, a->alpha, a->beta,
-                               dev_scalars(a), st), "crt");
+        rc = block_to_c(a, gp, take_fused(a), split, static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, sftA + row0, sftB + col0, st, &timer);
+        if (rc) return rc;
+        timer.finish(a->timers_ns);
+        return GEMMUL8_OK;
     }
     timer.mark();
     timer.finish(a->timers_ns);
@@ -815,12 +826,18 @@ int gemm_blocked_real(gemmul8_b200_args *a, const BlockPlan &P) {
             }
             timer.mark(0);
             gp.rowsA = r1 - r0; gp.rowsB = c1 - c0;
-            OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
-            timer.mark(1);
-            OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, r1 - r0, c1 - c0, C8u, P.mb_pad, P.sizeC,
-                                   static_cast<uint8_t *>(a->C) + (c0 * a->ldc + r0) * esC, a->ldc, sftA + r0, sftB + c0, a->alpha, a->beta, dev_scalars(a), st),
-                    "crt");
-            timer.mark(3);
+            void *Cblk = static_cast<uint8_t *>(a->C) + (c0 * a->ldc + r0) * esC;
+            if (take_fused(a)) {
+                int rc = block_to_c(a, gp, true, split, Cblk, sftA + r0, sftB + c0, st, nullptr);
+                if (rc) return rc;
+                timer.mark(1);
+            } else {
+                OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
+                timer.mark(1);
+                OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, r1 - r0, c1 - c0, C8u, P.mb_pad, P.sizeC, Cblk, a->ldc, sftA + r0, sftB + c0, a->alpha,
+                                       a->beta, dev_scalars(a), st), "crt");
+                timer.mark(3);
+            }
         }
     }
     timer.finish(a->timers_ns);

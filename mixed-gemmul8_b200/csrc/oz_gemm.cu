@@ -15,42 +15,27 @@
 //                             through a padded smem scratch, then 4-byte stores (4 rows of one column);
 //                             complex passes first combine with the stored residue (ResidueCombine),
 //                             whose words were prefetched before the accumulator became ready
-//   warps 8-11  epilogue too (columns 128-255 of the tile; warps 4-7 then take columns 0-127), except under
-//               EPI_CRT    : once a tile's last modulus is stored, re-read its residues
-//                             column-wise (128-byte rows per load, 28 loads in flight per lane),
-//                             CRT + mod M + inverse scaling + alpha/beta, 1 KiB stores of C
-// A work item is (C tile, modulus).  Two schedules:
-//   item-major (EPI_RESIDUE / EPI_INT32 / EPI_ABSMAX): items ordered (band of 16 row tiles, modulus,
-//       column tile, row tile); the ~148 items in flight share one modulus and a compact block of panels;
-//   tile-major (EPI_CRT): every CTA walks ALL moduli of its C tile (tiles ordered band / column / row,
-//       so the 148 tiles in flight still form a compact 16 x ~9 block that moves through the moduli
-//       together).  After the last modulus the CTA's four CRT warps read the tile's residue bytes
-//       back (L2-resident: 14 x 32 KiB per CTA), run the CRT accumulation + mod M + inverse scaling
-//       + alpha/beta (reference: GEMMul8/src/inverse_scaling.hpp:35-62,140-172) and write C, while
-//       the TMA / MMA / epilogue warps are already working through the next tile.  No separate CRT
-//       kernel, no second pass over HBM.
+//   warps 8-11  epilogue too (columns 128-255 of the tile; warps 4-7 then take columns 0-127)
+// A work item is (C tile, modulus), ordered (band of 16 row tiles, modulus, column tile, row tile): the ~148 items in
+// flight share one modulus and a compact block of panels.  (The single-kernel product + CRT lives in oz_gemm_crt.cu.)
 //
 // Both operands are K-major exactly as the reference lays them out (A8i[j][row][k], B8i[j][col][k],
 // row stride lda8i), so a 3-D tensor map (k, row, modulus) serves all moduli and K / row tails are
 // zero-filled by TMA.
-#include "oz_common.cuh"
-#include "oz_crt.cuh"
+#include "oz_tcgen05.cuh"
 
-#include <cuda.h>
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
 #include <vector>
-#include <cudaTypedefs.h>
 
 namespace oz {
+using namespace tc;
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 128;  // int8 elements == bytes == one 128B swizzle atom
-constexpr int UMMA_K  = 32;
 constexpr int STAGES  = 4;
 constexpr int SMEM_A  = BLOCK_M * BLOCK_K;
 constexpr int SMEM_B  = BLOCK_N * BLOCK_K;
@@ -61,107 +46,6 @@ constexpr int SMEM_TOTAL = STAGES * SMEM_STAGE + SMEM_BARRIERS + SMEM_SCRATCH + 
 constexpr int BAND_M = 16;  // row tiles per scheduling band
 constexpr int NUM_THREADS = 384;
 constexpr uint32_t TMEM_COLS = 512;
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The bound is wall time
-// (%globaltimer), 20 s: far beyond anything a time-sliced or co-scheduled kernel can be held up for, so it only ever
-// fires on a genuine deadlock.
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    unsigned long long t0 = 0;
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0xfffu) == 0) {
-            const unsigned long long now = global_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 20000000000ull) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, s8 x s8 -> s32
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// the same, with the loaded registers as in/out operands: every use of v is ordered after the wait by data flow, so
-// another tcgen05.ld may be in flight (software-pipelined epilogue) without relying on instruction order alone
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-                 :
-                 : "memory");
-}
-
-// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups (1024 B) are the
-// stride dimension; descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
-    d |= (uint64_t)0 << 16;                         // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
-    d |= (uint64_t)1 << 46;                         // version
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-    return d;
-}
-// instruction descriptor: D = s32, A = B = s8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t make_idesc(int M, int N) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct Sched {
     uint32_t tiles_m, tiles_n, slices, full_bands, per_band_full, total, band_m;
@@ -185,32 +69,19 @@ struct Sched {
 
 struct KernelArgs {
     uint32_t rowsA, rowsB, num_kb, first_modulus;
-    uint32_t tile_major, num_slices;
+    uint32_t num_slices;
     Sched sched;
     uint8_t *C8u; size_t ldc8u, sizeC; uint32_t rows_store;
     int combine; uint8_t *C8u_aux;
     int32_t *C32i; size_t ldc32i;
     int32_t *rowmax; int32_t *colmax;
-    // EPI_CRT
-    void *C; size_t ldc;
-    const int16_t *sftA; const int16_t *sftB;
-    double alpha, beta; int ab_mode;
 };
 
 // the it-th work item of this CTA; false when the CTA has run out of work
 __device__ __forceinline__ bool next_work(const KernelArgs &a, uint32_t it, uint32_t &tm, uint32_t &tn, uint32_t &j) {
-    uint32_t unit, jj = 0;
-    const uint32_t vb = blockIdx.x;
-    if (a.tile_major) {
-        const uint32_t t = it / a.num_slices;
-        jj   = it - t * a.num_slices;
-        unit = vb + t * gridDim.x;
-    } else {
-        unit = vb + it * gridDim.x;
-    }
+    const uint32_t unit = blockIdx.x + it * gridDim.x;
     if (unit >= a.sched.total) return false;
     a.sched.decode(unit, tm, tn, j);
-    j += jj;
     return true;
 }
 
@@ -263,7 +134,7 @@ __device__ __forceinline__ uint32_t combine_word(int rc, uint32_t rnew, uint32_t
     return fold_lanes(t0, m, k15) | (fold_lanes(t1, m, k15) << 8);
 }
 
-template <int EPI, typename T = double, bool SPLIT = false, bool RMW = false>
+template <int EPI, bool RMW = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const KernelArgs args) {
@@ -276,7 +147,6 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-    const uint32_t crt_full_bar = bar_base + 8u * (2 * STAGES + 5), crt_empty_bar = bar_base + 8u * (2 * STAGES + 6);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,9 +157,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_CRT ? 128 : 256); }
-        mbar_init(crt_full_bar, 128);
-        mbar_init(crt_empty_bar, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -344,7 +212,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 tcgen05_commit(tfull_bar(acc));  // accumulator complete
             }
         }
-    } else if (warp >= 4 && (warp < 8 || EPI != EPI_CRT)) {
+    } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         uint32_t tm, tn, j;
@@ -352,8 +220,8 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int rg = lane & 7, cg = lane >> 3;
         uint32_t *scr = reinterpret_cast<uint32_t *>(smem_raw + (bar_base + SMEM_BARRIERS - smem_u32(smem_raw))) + (warp - 4) * 160;
         // column chunks (16 wide) of the tile this warp drains: all 16, or one half each for the two epilogue groups
-        constexpr int NCH = EPI == EPI_CRT ? 16 : 8;
-        const int ch0     = EPI == EPI_CRT ? 0 : (warp >= 8 ? 8 : 0);
+        constexpr int NCH = 8;
+        const int ch0     = warp >= 8 ? 8 : 0;
         for (uint32_t it = 0; next_work(args, it, tm, tn, j); ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const uint32_t row  = tm * BLOCK_M + q * 32 + lane;
@@ -361,10 +229,10 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const bool row_ok   = row < args.rowsA;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
 
-            // EPI_RESIDUE / EPI_CRT state that does not depend on the accumulator
+            // EPI_RESIDUE state that does not depend on the accumulator
             const uint32_t row4 = tm * BLOCK_M + q * 32 + 4 * rg;
             const bool rows4_ok = row4 < args.rows_store;   // rowsA rounded up to 4 (the residue stacks are padded to 4 rows)
-            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4;       // (re-read under EPI_CRT: no __restrict__)
+            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4;
             uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4;
             uint32_t old[RMW ? 4 * NCH : 1];
             if constexpr (RMW) {   // complex passes: fetch the stored residues while the MMAs are still running
@@ -380,7 +248,7 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
 
-            if constexpr (EPI == EPI_RESIDUE || EPI == EPI_CRT) {
+            if constexpr (EPI == EPI_RESIDUE) {
                 const uint32_t mj  = args.first_modulus + j;
                 const int32_t m    = dev_tab::OZ_MOD[mj];
                 const int32_t inv  = (int32_t)(4294967296ull / (uint32_t)m);
@@ -460,79 +328,6 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(acc));  // the accumulator is free again: the MMA warp runs ahead
 
-            if constexpr (EPI == EPI_CRT) {
-                if (j + 1 == args.num_slices) {
-                    // hand the finished tile to the CRT warps (mbarrier arrive = release, their wait = acquire)
-                    const uint32_t t = it / args.num_slices;
-                    if (t > 0) mbar_wait(crt_empty_bar, (t - 1) & 1);
-                    mbar_arrive(crt_full_bar);
-                }
-            }
-        }
-    } else if (warp >= 8) {
-        // ===================== CRT warps =====================
-        if constexpr (EPI == EPI_CRT) {
-            const unsigned N = args.num_slices;
-            const int w      = warp - 8;
-            const T alpha = (T)args.alpha, beta = (T)args.beta;
-            uint32_t tm, tn, j;
-            for (uint32_t t = 0; next_work(args, t * N + (N - 1), tm, tn, j); ++t) {
-                mbar_wait(crt_full_bar, t & 1);
-                const uint32_t row0 = tm * BLOCK_M + 4 * lane;
-                const uint32_t col0 = tn * BLOCK_N;
-                const uint32_t ncol = min((uint32_t)BLOCK_N, args.rowsB - col0);
-                if (row0 < args.rowsA) {
-                    int sa[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sa[e] = (row0 + e < args.rowsA) ? (int)args.sftA[row0 + e] : 0;
-                    const uint8_t *res = args.C8u + row0;
-                    T *crow            = static_cast<T *>(args.C) + row0;
-#pragma unroll 1
-                    for (uint32_t c = 2 * w; c < ncol; c += 8) {   // two columns per step and warp
-                        const bool two = c + 1 < ncol;
-                        const uint8_t *src0 = res + (size_t)(col0 + c) * args.ldc8u;
-                        const uint8_t *src1 = src0 + (two ? args.ldc8u : 0);
-                        uint32_t r0[kMaxModuli], r1[kMaxModuli];
-#pragma unroll
-                        for (int jj = 0; jj < kMaxModuli; ++jj) {
-                            if (jj < (int)N) {
-                                r0[jj] = __ldcg(reinterpret_cast<const uint32_t *>(src0 + (size_t)jj * args.sizeC));
-                                r1[jj] = __ldcg(reinterpret_cast<const uint32_t *>(src1 + (size_t)jj * args.sizeC));
-                            }
-                        }
-                        double s1[8], s2[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) { s1[e] = 0.0; s2[e] = 0.0; }
-#pragma unroll
-                        for (int jj = 0; jj < kMaxModuli; ++jj) {
-                            if (jj < (int)N) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    crt_step<SPLIT>(N, jj, (r0[jj] >> (8 * e)) & 0xffu, s1[e], s2[e]);
-                                    crt_step<SPLIT>(N, jj, (r1[jj] >> (8 * e)) & 0xffu, s1[4 + e], s2[4 + e]);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            if (cc == 0 || two) {
-                                const uint32_t col = col0 + c + cc;
-                                const int sb       = (int)args.sftB[col];
-                                T *cptr            = crow + (size_t)col * args.ldc;
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    if (row0 + e < args.rowsA) {
-                                        const double v = scale_pow2(crt_finish<SPLIT>(N, s1[4 * cc + e], s2[4 * cc + e]), sa[e] + sb);
-                                        cptr[e] = combine<T>(args.ab_mode, alpha, beta, cast_out<T>(v), cptr + e);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(crt_empty_bar);
-            }
         }
     }
 
@@ -568,56 +363,6 @@ constexpr int PAIR_THREADS   = (4 + PAIR_EPI_WARPS) * 32;
 constexpr int PAIR_SCRATCH   = PAIR_EPI_WARPS * 32 * 5 * 4;
 constexpr int pair_smem_total(int stages) { return stages * PAIR_STAGE + SMEM_BARRIERS + PAIR_SCRATCH + 1024; }
 constexpr int PAIR_BAND = 8;                            // 256-row tiles per scheduling band
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-// The "accumulator drained" signal hands over tensor memory, not data in global or shared memory: the tcgen05.ld of
-// this warp have completed (tcgen05.wait::ld) and are fenced (tcgen05.fence::before_thread_sync) when it is sent.  A
-// release at cluster scope would also wait for the warp's residue STOREs to be acknowledged (MEMBAR.GPU + ERRBAR,
-// 8 % of the epilogue's time at k = 2048) before the MMA warp may reuse the buffer.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// x mod m in [0, m) for |x| <= 2^17 * 127^2 (every modulus but 256 has |residue| <= 127, k <= 2^17): shift x by a
-// multiple of m into the unsigned range, q = umulhi(x', floor(2^32 / m)) is floor(x' / m) or one less, ONE correction
-constexpr uint32_t kMaxAbsProduct = 2114060288u;   // 2^17 * 127^2
-__device__ __forceinline__ uint32_t reduce_mod_u(int32_t x, uint32_t m, uint32_t inv, uint32_t off) {
-    const uint32_t xu = (uint32_t)x + off;
-    uint32_t r = xu - __umulhi(xu, inv) * m;
-    r -= (r >= m) ? m : 0u;
-    return r;
-}
-// TMA load into this CTA's shared memory; the transaction bytes land on the barrier at `bar_cluster_addr`
-__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 
 struct PairSched {   // items = (256-row tile, column tile, modulus), ordered (band of 8 row tiles, modulus, column tile, row tile)
     uint32_t tiles_m, tiles_n, slices, full_bands, per_band_full, total, band_m;
@@ -674,17 +419,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // slots: each slot is worked exactly once whatever the placement.
     const uint32_t pair_slot = bar_base + 8u * (2 * NSTAGES + 5);
     if (warp == 1 && lane == 0 && rank == 0) {
-        uint32_t pair = blockIdx.x >> 1;
-        if (args.slot != nullptr) {
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            uint32_t want = args.slot[smid] >> 1;
-            if (want >= npairs) want = pair;
-            for (uint32_t i = 0; i < npairs; ++i) {
-                const uint32_t c = want + i < npairs ? want + i : want + i - npairs;
-                if (atomicCAS(args.claims + c, 0u, 1u) == 0u) { pair = c; break; }
-            }
-        }
+        const uint32_t pair = claim_pair_slot(args.slot, args.claims, npairs, blockIdx.x >> 1);
         asm volatile("st.shared::cta.u32 [%0], %1;" ::"r"(pair_slot), "r"(pair) : "memory");   // read by both CTAs after the cluster barrier
     }
 
@@ -885,6 +620,10 @@ __global__ void oz_gemm_simt_kernel(const int8_t *__restrict__ A8i, const int8_t
     }
 }
 
+}  // namespace
+
+namespace detail {
+namespace {
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
     static const PFN_cuTensorMapEncodeTiled_v12000 fn = [] {   // initialised once, thread-safe
         void *p = nullptr;
@@ -896,6 +635,7 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
     }();
     return fn;
 }
+}  // namespace
 
 // (k, row, slice) view of a stack of K-major int8 slices; box = 128 bytes of k x box_rows rows
 bool make_operand_map(CUtensorMap *map, const int8_t *base, size_t ld8i, size_t rows, size_t slices, size_t slice_stride,
@@ -911,19 +651,20 @@ bool make_operand_map(CUtensorMap *map, const int8_t *base, size_t ld8i, size_t 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+}  // namespace detail
 
-KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
+namespace {
+using detail::make_operand_map;
+
+KernelArgs make_args(const GemmProblem &p) {
     KernelArgs a{};
     a.rowsA = (uint32_t)p.rowsA; a.rowsB = (uint32_t)p.rowsB;
     a.num_kb = (uint32_t)((p.ld8i + BLOCK_K - 1) / BLOCK_K);
     a.first_modulus = p.first_modulus;
     a.num_slices = p.num_slices;
-    a.tile_major = tile_major ? 1u : 0u;
     const int band = tuning().band;
     a.sched.init((uint32_t)((p.rowsA + BLOCK_M - 1) / BLOCK_M), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N),
-                 tile_major ? 1u : p.num_slices, band > 0 ? (uint32_t)band : (uint32_t)BAND_M);
-    a.C = p.C; a.ldc = p.ldc; a.sftA = p.sftA; a.sftB = p.sftB; a.alpha = p.alpha; a.beta = p.beta;
-    a.ab_mode = alpha_beta_mode(p.alpha, p.beta);
+                 p.num_slices, band > 0 ? (uint32_t)band : (uint32_t)BAND_M);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
     a.rows_store = (uint32_t)((p.rowsA + 3) / 4 * 4);   // a sub-block launch must not touch the rows below it
     a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
@@ -932,6 +673,9 @@ KernelArgs make_args(const GemmProblem &p, bool tile_major = false) {
     return a;
 }
 
+}  // namespace
+
+namespace detail {
 constexpr int kMaxDevices = 64;
 int current_device() {
     int dev = 0;
@@ -948,14 +692,24 @@ int sm_count() {   // of the current device (cached: an attribute query per laun
     }
     return n;
 }
+bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+}
+}  // namespace detail
 
-template <int EPI, typename T = double, bool SPLIT = false, bool RMW = false>
+namespace {
+using detail::sm_count;
+using detail::kMaxDevices;
+using detail::current_device;
+
+template <int EPI, bool RMW = false>
 cudaError_t launch_tc(const GemmProblem &p, cudaStream_t st) {
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, BLOCK_M)) return cudaErrorInvalidValue;
     if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, BLOCK_N)) return cudaErrorInvalidValue;
-    KernelArgs a = make_args(p, EPI == EPI_CRT);
-    auto kern = oz_gemm_tcgen05_kernel<EPI, T, SPLIT, RMW>;
+    KernelArgs a = make_args(p);
+    auto kern = oz_gemm_tcgen05_kernel<EPI, RMW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const uint32_t grid = a.sched.total < (uint32_t)sm_count() ? a.sched.total : (uint32_t)sm_count();
@@ -1009,8 +763,9 @@ const uint32_t *probe_placement(int n) {
 }
 struct Placement { std::mutex mu; std::atomic<int> state{0}; const uint32_t *table = nullptr; };   // state: 0 unknown, 1 probed
 Placement g_placement[kMaxDevices];
+}  // namespace
 
-const uint32_t *placement_slots(bool allow_probe) {
+const uint32_t *detail::placement_slots(bool allow_probe) {
     const int dev = current_device();
     if (dev < 0 || dev >= kMaxDevices) return nullptr;
     Placement &P = g_placement[dev];
@@ -1025,6 +780,9 @@ const uint32_t *placement_slots(bool allow_probe) {
     return P.table;
 }
 
+namespace {
+using detail::placement_slots;
+
 // CTA-pair kernel for EPI_RESIDUE (all combine modes).  Default whenever the placement table exists (whole GPU, even SM
 // count); option gemm_pair = 0 selects the single-CTA kernel, 1 forces the pair kernel even without the table.
 // Measured at 16384^3, 14 moduli, same box: single-CTA 46.7 / 48.7 ms, pairs placed by block index 53.9 - 57.2 ms,
@@ -1034,9 +792,7 @@ bool pair_kernel_enabled(cudaStream_t st) {
     if (mode == 0) return false;
     if (sm_count() < 2 || (sm_count() & 1)) return false;
     if (mode == 1) return true;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
-    return placement_slots(!capturing) != nullptr;
+    return placement_slots(!detail::stream_is_capturing(st)) != nullptr;
 }
 template <bool RMW>
 cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
@@ -1076,7 +832,7 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
 }  // namespace
 
 void gemm_prepare_device(bool allow_probe) {
-    if (tuning().gemm_pair != 0) placement_slots(allow_probe);
+    if (tuning().gemm_pair != 0) detail::placement_slots(allow_probe);
 }
 
 cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStream_t st) {
@@ -1084,12 +840,10 @@ cudaError_t launch_gemm_tcgen05(const GemmProblem &p, GemmEpilogue epi, cudaStre
     switch (epi) {
         case EPI_RESIDUE:
             if (pair_kernel_enabled(st)) return p.combine == RC_STORE ? launch_pair<false>(p, st) : launch_pair<true>(p, st);
-            return p.combine == RC_STORE ? launch_tc<EPI_RESIDUE>(p, st) : launch_tc<EPI_RESIDUE, double, false, true>(p, st);
+            return p.combine == RC_STORE ? launch_tc<EPI_RESIDUE>(p, st) : launch_tc<EPI_RESIDUE, true>(p, st);
         case EPI_INT32:   return launch_tc<EPI_INT32>(p, st);
         case EPI_ABSMAX:  return launch_tc<EPI_ABSMAX>(p, st);
-        case EPI_CRT:
-            if (p.dtype_C == DT_F32) return launch_tc<EPI_CRT, float, false>(p, st);
-            return p.split_weights ? launch_tc<EPI_CRT, double, true>(p, st) : launch_tc<EPI_CRT, double, false>(p, st);
+        case EPI_CRT:     return launch_gemm_crt(p, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -154,3 +154,20 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"liboracle|oracle\.py|import oracle|oracle/_ref|libgemmul8_ref", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_options_api_without_a_device(g):
+    """set_option / get_option are host state; init() needs a device and says so (no CPU fallback)."""
+    assert g.get_option("gemm_pair") in (-1, 0, 1)
+    old = g.get_option("pair_band")
+    g.set_option("pair_band", 4)
+    assert g.get_option("pair_band") == 4
+    g.set_option("pair_band", old)
+    with pytest.raises(g.Gemmul8Error):
+        g.set_option("no_such_option", 1)
+    with pytest.raises(g.Gemmul8Error):
+        g.set_option("gemm_pair", 7)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(g.Gemmul8Error):
+            g.init()

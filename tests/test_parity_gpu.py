@@ -222,17 +222,21 @@ def test_tcgen05_gemm_equals_cuda_core_gemm(g):
     (300, 515, 256, 7, "float64", 0.5, 2.0),        # single weights, general alpha/beta
     (129, 257, 130, 6, "float32", 1.0, 1.0),        # fp32 output
     (2048, 4096, 512, 20, "float64", 1.0, 0.0),     # more tiles than SMs x 1, 20 moduli
+    (4100, 9500, 384, 14, "float64", 1.0, 0.0),     # more tiles than CTA pairs (placed path), ragged in both directions
+    (1000, 777, 3000, 2, "float64", 1.0, 0.0),      # the fewest moduli
+    (513, 97, 5000, 8, "float64", -1.0, 0.5),       # first split-weight count, one column past a tile
+    (260, 200, 640, 12, "float32", 2.0, 0.0),       # fp32 output, single weights with N > 7
 ])
 def test_fused_crt_equals_unfused(g, m, n, k, N, dt, alpha, beta):
-    """The single-kernel variant (CRT warps behind the last modulus, tile-major schedule; FLAG_FUSED_CRT)
-    against the default residues-to-HBM + stand-alone CRT kernel (item-major schedule): bit-identical."""
+    """The single kernel (oz_gemm_crt.cu: product, residues, CRT accumulators in registers across the modulus walk, inverse
+    scaling, alpha / beta; FLAG_FUSED_CRT forces it) against product + residues to HBM + the stand-alone CRT kernel: C bit for bit."""
     torch = torch_()
     A, B = operands(g, m, n, k, 0, 0, getattr(torch, dt), getattr(torch, dt), seedB=77)
     C0 = g.phi_matrix(m, n, 1.0, getattr(torch, dt), seed=5)
     C_f, v_f = run_ours(g, m, n, k, N, True, A, B, alpha=alpha, beta=beta, C0=C0, flags=g.FLAG_FUSED_CRT)
     C_u, v_u = run_ours(g, m, n, k, N, True, A, B, alpha=alpha, beta=beta, C0=C0)
-    assert torch.equal(v_f["C8u"][:, :, :m], v_u["C8u"][:, :, :m])
     assert torch.equal(C_f, C_u)
+    assert torch.equal(v_f["A8i"], v_u["A8i"]) and not v_f["C8u"].any()     # same slices in; the single kernel leaves no residues in HBM
 
 
 def test_encoder_routes_equal_reference_instruction_sequence(g, monkeypatch):
@@ -597,3 +601,25 @@ def test_benchmark_size_properties(g):
     sub = C[ci.long()][:, ri.long()]
     err = ((sub - C1 - C2) / C1).abs()
     assert err.median().item() < 1e-12 and err.max().item() < 1e-3
+
+
+def test_fused_path_is_selected_by_k(g):
+    """Option "fused_k": calls with k at or below it take the single kernel without being asked (same bits, no residues in HBM)."""
+    torch = torch_()
+    m, n, k, N = 1500, 1100, 512, 14
+    A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=3)
+    old = g.get_option("fused_k")
+    try:
+        g.set_option("fused_k", 0)
+        C_u, v_u = run_ours(g, m, n, k, N, True, A, B)
+        g.set_option("fused_k", 512)
+        C_f, v_f = run_ours(g, m, n, k, N, True, A, B)
+        C_a, _ = run_ours(g, m, n, k, N, False, A, B)            # accurate mode through the same kernel
+        g.set_option("fused_k", 511)
+        C_2, v_2 = run_ours(g, m, n, k, N, True, A, B)
+        g.set_option("fused_k", 0)
+        C_b, _ = run_ours(g, m, n, k, N, False, A, B)
+    finally:
+        g.set_option("fused_k", old)
+    assert torch.equal(C_f, C_u) and torch.equal(C_2, C_u) and torch.equal(C_a, C_b)
+    assert v_u["C8u"].any() and not v_f["C8u"].any() and v_2["C8u"].any()

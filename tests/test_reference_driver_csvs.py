@@ -61,3 +61,25 @@ def test_timing_rows_carry_identical_errors_and_are_faster():
             assert float(o["TFLOPS"]) > float(r["TFLOPS"]), key
             n += 1
         assert n == rows
+
+
+DIR2 = os.path.join(ROOT, "profiles", "r02_reference_drivers")
+
+
+def test_round2_drivers_accuracy_tables_identical_between_libraries():
+    """test_mixed_double (FP64 x FP32 -> FP64), test_mixed_float (-> FP32) and test_float_complex, the three drivers round 1 only
+    built (GEMMul8/testing/test_mixed_double.cu:162, test_mixed_float.cu:200, test_float_complex.cu:24,201): every emulation
+    cell of their accuracy tables -- 5 phi x 4 k x 2..20 moduli x fast / accurate -- is the same string with both libraries."""
+    t = _tool()
+    for prec, cells in (("dfd", 760), ("dff", 448), ("fC", 448)):
+        def one(lib):
+            c = glob.glob(os.path.join(DIR2, f"{lib}_oz2_results_{prec}_accuracy_*.csv"))
+            assert len(c) == 1, c
+            return t.accuracy_table(t.read_csv(c[0]))[0]
+        ours, ref = one("ours"), one("ref")
+        n = 0
+        for key, row in ours.items():
+            if t.is_emulation(key[1]):
+                assert row == ref[key], (prec, key)
+                n += len(row)
+        assert n == cells

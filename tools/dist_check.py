@@ -12,15 +12,13 @@ import gemmul8_b200 as g
 from importlib import import_module
 
 
-def main():
-    S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dmod = import_module("gemmul8_b200.distributed")
-    grid = dmod.BlockGrid()
+def run_checks(grid, dmod, S=2048, verbose=True, pgemm=None):
+    """The three comparisons, on every rank; returns a dict (ok, per-case details).  `pgemm` defaults to
+    distributed.pgemm (bench.py passes the entry point it timed)."""
+    pgemm = pgemm or dmod.pgemm
     rank = dist.get_rank()
     ok = True
+    details = []
     for (m, n, k, N) in ((S * grid.P, S * grid.Q, S, 14), (grid.P * 1280, grid.Q * 768, 4 * 640, 9)):
         m_loc, n_loc = grid.block_dims(m, n)
         klo, khi = grid.a_slice_k(k)
@@ -30,7 +28,7 @@ def main():
         work = torch.empty(g.workSize(m_loc, n_loc, k, N), dtype=torch.uint8, device="cuda")
         C1 = torch.zeros((n_loc, m_loc), dtype=torch.float64, device="cuda")
         C2 = torch.full_like(C1, 7.0)
-        dmod.pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, C1, N, True, work)                       # pipelined
+        pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, C1, N, True, work)                            # pipelined
         dmod.pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, C2, N, True, work, flags=g.FLAG_TIMERS)  # plain
         torch.cuda.synchronize()
         same = torch.equal(C1, C2) and bool(C1.abs().sum() > 0)
@@ -42,12 +40,13 @@ def main():
         T1, T2 = g.dd_gemm(m_loc, n_loc, k, a_panel, m_loc, b_panel, k, rows=rows, cols=cols)
         err = (((C1[cols.long()][:, rows.long()] - T1) - T2) / T1).abs().max().item()
         good = same and err < (1e-6 if N >= 14 else 1e-3)      # 9 moduli carry ~1e-5 by construction
-        print(f"rank {rank} grid {grid.P}x{grid.Q} block ({grid.p},{grid.q}) m={m} n={n} k={k} N={N}: identical={same} relerr_max={err:.3e}", flush=True)
+        if verbose:
+            print(f"rank {rank} grid {grid.P}x{grid.Q} block ({grid.p},{grid.q}) m={m} n={n} k={k} N={N}: identical={same} relerr_max={err:.3e}", flush=True)
         ok = ok and good
         # accurate mode: the partitioned call (bound maxima combined over the grid row / column) against the
         # UNPARTITIONED accurate product of the full matrices, computed here on every rank: its block, bit for bit
         C3 = torch.zeros_like(C1)
-        dmod.pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, C3, N, False, work)
+        pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, C3, N, False, work)
         if grid.P > 1:
             parts = [torch.empty_like(a_panel) for _ in range(grid.P)]
             dist.all_gather(parts, a_panel.contiguous(), group=grid.col_group)
@@ -66,15 +65,30 @@ def main():
         torch.cuda.synchronize()
         blk = Cf[grid.q * n_loc:(grid.q + 1) * n_loc, grid.p * m_loc:(grid.p + 1) * m_loc]
         acc_same = torch.equal(C3, blk) and bool(C3.abs().sum() > 0)
-        print(f"rank {rank} accurate mode, block of the unpartitioned product: identical={acc_same}", flush=True)
+        if verbose:
+            print(f"rank {rank} accurate mode, block of the unpartitioned product: identical={acc_same}", flush=True)
         ok = ok and acc_same
+        details.append({"m": m, "n": n, "k": k, "moduli": N, "pipelined_equals_plain": bool(same), "relerr_max_vs_dd": err,
+                        "accurate_block_equals_unpartitioned": bool(acc_same)})
+        del Cf, wf, A_full, B_full, work
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
-    if rank == 0:
-        print("DIST OK" if flag.item() == 0 else "DIST FAILED", flush=True)
+    return {"ok": flag.item() == 0, "ranks": dist.get_world_size(), "cases_rank0": details}
+
+
+def main():
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dmod = import_module("gemmul8_b200.distributed")
+    grid = dmod.BlockGrid()
+    res = run_checks(grid, dmod, S)
+    if dist.get_rank() == 0:
+        print("DIST OK" if res["ok"] else "DIST FAILED", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    return 0 if flag.item() == 0 else 1
+    return 0 if res["ok"] else 1
 
 
 if __name__ == "__main__":
