@@ -13,7 +13,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgemmul8_b200.so")
+# (GEMMUL8_B200_LIB: another build of the same library, for A/B timing of kernel variants inside one GPU visit)
+LIB_PATH = os.environ.get("GEMMUL8_B200_LIB") or os.path.join(_HERE, "libgemmul8_b200.so")
 AUX_PATH = os.path.join(_HERE, "libgemmul8_b200_aux.so")
 
 # gemmul8::computeType_t (GEMMul8/include/gemmul8.hpp:7-12)

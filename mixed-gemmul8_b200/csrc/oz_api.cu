@@ -31,8 +31,8 @@ struct Option { const char *name; const char *env; std::atomic<int> value; int l
 Option g_options[] = {
     {"gemm_pair", "OZ_GEMM_PAIR", {-1}, -1, 1},
     {"band", "OZ_BAND", {16}, 1, 1024},
-    {"pair_band", "OZ_PAIR_BAND", {8}, 1, 1024},
-    {"pair_stages", "OZ_PAIR_STAGES", {0}, 0, 6},
+    {"pair_band", "OZ_PAIR_BAND", {0}, 0, 4096},
+    {"pair_stages", "OZ_PAIR_STAGES", {0}, 0, 7},
     {"encode_reference", nullptr, {0}, 0, 1},
     {"fused_k", "GEMMUL8_B200_FUSED_K", {0}, 0, 1 << 17},
 };

@@ -354,13 +354,22 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 //   every CTA    warp 2 : TMEM allocation (cta_group::2), warps 4-11: epilogue of its own 128 rows;
 //                         one lane per warp tells the leader that the accumulator buffer is drained
 // =============================================================================================
-constexpr int PAIR_STAGES = 6;
+#ifndef OZ_EPI_DRAIN_FIRST
+#define OZ_EPI_DRAIN_FIRST 1   // A/B knob of tools/ab_build.sh; 0 = read and reduce the slab in two halves
+#endif
+#ifndef OZ_EPI_STORE256
+#define OZ_EPI_STORE256 1      // A/B knob: 0 = two 128-bit stores per 32-byte run
+#endif
+#ifndef OZ_PAIR_STAGES_DEFAULT
+#define OZ_PAIR_STAGES_DEFAULT 6
+#endif
+constexpr int PAIR_STAGES = OZ_PAIR_STAGES_DEFAULT;
 constexpr int PAIR_SMEM_A = BLOCK_M * BLOCK_K;          // 128 rows of A
 constexpr int PAIR_SMEM_B = 128 * BLOCK_K;              // 128 of the tile's 256 columns of B
 constexpr int PAIR_STAGE  = PAIR_SMEM_A + PAIR_SMEM_B;  // 32 KiB per CTA and stage
 constexpr int PAIR_EPI_WARPS = 16;                      // 4 per TMEM lane quarter, 64 of the tile's 256 columns each
 constexpr int PAIR_THREADS   = (4 + PAIR_EPI_WARPS) * 32;
-constexpr int PAIR_SCRATCH   = PAIR_EPI_WARPS * 32 * 5 * 4;
+constexpr int PAIR_SCRATCH   = 0;                       // (the epilogue needs no shared memory any more)
 constexpr int pair_smem_total(int stages) { return stages * PAIR_STAGE + SMEM_BARRIERS + PAIR_SCRATCH + 1024; }
 constexpr int PAIR_BAND = 8;                            // 256-row tiles per scheduling band
 
@@ -448,8 +457,8 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, tm, tn, j;
             for (uint32_t item = pair; item < total; item += npairs) {
-                args.sched.decode(item, tm, tn, j);
-                const int rowA = (int)(tm * 256 + rank * 128), rowB = (int)(tn * BLOCK_N + rank * 128);
+                args.sched.decode(item, tm, tn, j);      // tm: 256-column tile of C (MMA M side), tn: 256-row tile of C (MMA N side)
+                const int rowA = (int)(tm * 256 + rank * 128), rowB = (int)(tn * BLOCK_N + rank * 128);   // map_a = B8i, map_b = A8i
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa   = smem_base + stage * PAIR_STAGE;
@@ -486,98 +495,136 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (both CTAs, own 128 rows) =====================
-        // 16 warps: warp & 3 = TMEM lane quarter (32 rows), (warp - 4) >> 2 = 64-column group, 4 chunks of 16 columns.
-        // With short k the kernel is bound by this loop, not by the MMA (k = 2048: 8 warps kept the tensor pipe at
-        // 49 %), so it is built for issue slots: unsigned Barrett with one correction, the modulus-256 case hoisted,
-        // interior tiles without bounds checks, running store pointers.
-        const int q = warp & 3, colgroup = (warp - 4) >> 2;
-        const int rg = lane & 7, cg = lane >> 3;
-        uint32_t *scr = reinterpret_cast<uint32_t *>(smem_raw + (bar_base + SMEM_BARRIERS - smem_u32(smem_raw))) + (warp - 4) * 160;
-        constexpr int NCH = 4;
-        const int ch0     = NCH * colgroup;
+        // ===================== epilogue (both CTAs, own 128 COLUMNS of C) =====================
+        // The operand roles are swapped with respect to C = A B: the "M side" of the MMA (tensor-memory lanes, split over
+        // the two CTAs) holds rows of B8i, i.e. COLUMNS of C, and the "N side" (tensor-memory columns) rows of A8i, i.e.
+        // ROWS of C.  A thread (lane == one column of C) therefore reads 32 consecutive rows of its column with one
+        // tcgen05.ld -- exactly 32 consecutive bytes of the column-major residue matrix: Barrett, pack, two 16-byte stores.
+        // No transpose through shared memory, no __syncwarp (the 9.4 instructions per residue of the row-major version
+        // were what bounded the kernel below k ~ 2048; this is ~5).
+        // 16 warps: warp & 3 = TMEM lane quarter (32 columns of C), (warp - 4) >> 2 = 64-row group, 2 chunks of 32 rows.
+        const int q = warp & 3, rowgroup = (warp - 4) >> 2;
+        constexpr int NCH = 2;
         const size_t ld   = args.ldc8u;
-        uint32_t tm, tn, j, it = 0;
+        const bool vec_ok = (ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(args.C8u) | (uintptr_t)args.sizeC) % 16 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(args.C8u_aux)) % 16 == 0);
+        // 32 contiguous bytes per lane as ONE 256-bit store where the addresses allow it: a warp's store touches 32 different
+        // lines (lane == column), so every store instruction costs 32 LSU wavefronts whatever its width
+        const bool vec32_ok = vec_ok && OZ_EPI_STORE256 && (ld % 32 == 0) && ((reinterpret_cast<uintptr_t>(args.C8u) | (uintptr_t)args.sizeC) % 32 == 0);
+        uint32_t tu, tv, j, it = 0;
         for (uint32_t item = pair; item < total; item += npairs, ++it) {
-            args.sched.decode(item, tm, tn, j);
+            args.sched.decode(item, tu, tv, j);
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const uint32_t col0 = tn * BLOCK_N + 16 * ch0 + 4 * cg;     // this lane's first column
-            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16) + 16 * ch0;
-            const uint32_t row4 = tm * 256 + rank * 128 + q * 32 + 4 * rg;
-            const bool rows4_ok = row4 < args.rows_store;
-            const bool interior = (tm * 256 + 256 <= args.rows_store) && (tn * BLOCK_N + BLOCK_N <= args.rowsB);
-            uint8_t *out4 = args.C8u + (size_t)j * args.sizeC + row4 + (size_t)col0 * ld;
-            uint8_t *aux4 = args.C8u_aux + (size_t)j * args.sizeC + row4 + (size_t)col0 * ld;
-            uint32_t old[RMW ? 4 * NCH : 1];
-            if constexpr (RMW) {
+            const uint32_t col  = tu * 256 + rank * 128 + q * 32 + lane;           // this lane's column of C
+            const uint32_t row0 = tv * BLOCK_N + 64 * rowgroup;                    // first of this warp's 64 rows of C
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16) + 64 * rowgroup;
+            const bool col_ok   = col < args.rowsB;
+            const bool interior = vec_ok && (row0 + 64 <= args.rows_store);
+            uint8_t *out = args.C8u + (size_t)j * args.sizeC + (size_t)col * ld + row0;
+            uint8_t *aux = args.C8u_aux + (size_t)j * args.sizeC + (size_t)col * ld + row0;
+            uint32_t old[RMW ? 8 * NCH : 1];
+            if constexpr (RMW) {   // complex passes: fetch the stored residues while the MMAs are still running
 #pragma unroll
-                for (int c = 0; c < NCH; ++c)
+                for (int c = 0; c < NCH; ++c) {
+                    if (interior && col_ok) {
+                        const uint4 a0 = __ldcg(reinterpret_cast<const uint4 *>(out + 32 * c)), a1 = __ldcg(reinterpret_cast<const uint4 *>(out + 32 * c + 16));
+                        old[8 * c + 0] = a0.x; old[8 * c + 1] = a0.y; old[8 * c + 2] = a0.z; old[8 * c + 3] = a0.w;
+                        old[8 * c + 4] = a1.x; old[8 * c + 5] = a1.y; old[8 * c + 6] = a1.z; old[8 * c + 7] = a1.w;
+                    } else {
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const uint32_t col = col0 + 16 * c + jj;
-                        old[4 * c + jj] = (rows4_ok && col < args.rowsB) ? __ldcg(reinterpret_cast<const uint32_t *>(out4 + (size_t)(16 * c + jj) * ld)) : 0u;
+                        for (int w = 0; w < 8; ++w)
+                            old[8 * c + w] = (col_ok && row0 + 32 * c + 4 * w < args.rows_store) ? __ldcg(reinterpret_cast<const uint32_t *>(out + 32 * c + 4 * w)) : 0u;
                     }
+                }
             }
             const uint32_t mj = args.first_modulus + j;
             const uint32_t m  = (uint32_t)dev_tab::OZ_MOD[mj];
-            const uint32_t inv = (uint32_t)(4294967296ull / m);
-            const uint32_t off = m * ((kMaxAbsProduct + m - 1) / m);
+            const uint32_t inv = dev_tab::OZ_BARRETT_INV[mj], negm = dev_tab::OZ_BARRETT_NEGM[mj];
+            const uint32_t off = dev_tab::OZ_BARRETT_OFF[mj];
             const int rc       = args.combine;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
+            // Plain passes read the whole 64-row slab into registers at once and hand the accumulator buffer back BEFORE any
+            // arithmetic: with short k the MMA of item i + 2 waits for exactly this signal (two buffers), so every cycle
+            // between "accumulator complete" and "drained" is a cycle the tensor pipe may idle.  The combine passes carry
+            // the stored residues in registers as well and read the slab in two halves.
+            constexpr bool DRAIN_FIRST = !RMW && OZ_EPI_DRAIN_FIRST;
+            uint32_t v2[DRAIN_FIRST ? NCH : 1][32];
+            if constexpr (DRAIN_FIRST) {
+#ifdef OZ_DBG_NO_LDTM   // experiment builds only (tools/ab_build.sh): what bounds the epilogue?
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v2[c][e] = taddr * (e + 1) + c;
+#else
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tmem_ld32(taddr + 32 * c, v2[c]);
+                tmem_ld_wait(v2[0], v2[1]);
+#endif
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(tempty_bar(acc), 0));
+            }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                uint32_t v[16];
-                tmem_ld16(taddr + 16 * c, v);
-                tmem_ld_wait(v);
-                uint32_t pk[4];
-                if (mj == 0) {          // modulus 256: the low byte (the only product that may wrap)
-#pragma unroll
-                    for (int w = 0; w < 4; ++w)
-                        pk[w] = __byte_perm(__byte_perm(v[4 * w], v[4 * w + 1], 0x0040), __byte_perm(v[4 * w + 2], v[4 * w + 3], 0x0040), 0x5410);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = reduce_mod_u((int32_t)v[e], m, inv, off);
-#pragma unroll
-                    for (int w = 0; w < 4; ++w)
-                        pk[w] = __byte_perm(__byte_perm(v[4 * w], v[4 * w + 1], 0x0040), __byte_perm(v[4 * w + 2], v[4 * w + 3], 0x0040), 0x5410);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int w = 0; w < 4; ++w) scr[5 * lane + w] = pk[w];
-                __syncwarp();
-                const uint32_t w0 = scr[5 * (4 * rg) + cg], w1 = scr[5 * (4 * rg + 1) + cg];
-                const uint32_t w2 = scr[5 * (4 * rg + 2) + cg], w3 = scr[5 * (4 * rg + 3) + cg];
-                const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
-                const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
-                uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
-                                 __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
-                uint8_t *po = out4 + (size_t)(16 * c) * ld;
-                if constexpr (!RMW) {
-                    if (interior) {
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint32_t *>(po + (size_t)jj * ld) = o[jj];
-                        continue;
+                uint32_t vr[DRAIN_FIRST ? 1 : 32];
+                if constexpr (!DRAIN_FIRST) {
+                    tmem_ld32(taddr + 32 * c, vr);
+                    tmem_ld_wait(vr);
+                    if (c == NCH - 1) {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(tempty_bar(acc), 0));
                     }
                 }
-                if (rows4_ok) {
+                uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(DRAIN_FIRST ? v2[DRAIN_FIRST ? c : 0] : vr);
+#ifdef OZ_DBG_NO_BARRETT
+                if (false) {
+#else
+                if (mj != 0) {          // (modulus 256: the low byte, which the packing below takes anyway)
+#endif
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const uint32_t col = col0 + 16 * c + jj;
-                        if (col < args.rowsB) {
-                            if constexpr (RMW) {
-                                uint32_t ax;
-                                o[jj] = combine_word(rc, o[jj], old[4 * c + jj], ax, (int32_t)m);
-                                if (rc == RC_KARATSUBA_F) *reinterpret_cast<uint32_t *>(aux4 + (size_t)(16 * c + jj) * ld) = ax;
-                            }
-                            *reinterpret_cast<uint32_t *>(po + (size_t)jj * ld) = o[jj];
+                    for (int e = 0; e < 32; ++e) v[e] = reduce_mod_u((int32_t)v[e], negm, inv, off);
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    pk[w] = __byte_perm(__byte_perm(v[4 * w], v[4 * w + 1], 0x0040), __byte_perm(v[4 * w + 2], v[4 * w + 3], 0x0040), 0x5410);
+                if (!col_ok) continue;
+                uint8_t *po = out + 32 * c, *pa = aux + 32 * c;
+                if constexpr (RMW) {
+                    uint32_t ax[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) pk[w] = combine_word(rc, pk[w], old[8 * c + w], ax[w], (int32_t)m);
+                    if (rc == RC_KARATSUBA_F) {
+                        if (interior) {
+                            *reinterpret_cast<uint4 *>(pa)      = make_uint4(ax[0], ax[1], ax[2], ax[3]);
+                            *reinterpret_cast<uint4 *>(pa + 16) = make_uint4(ax[4], ax[5], ax[6], ax[7]);
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < 8; ++w)
+                                if (row0 + 32 * c + 4 * w < args.rows_store) *reinterpret_cast<uint32_t *>(pa + 4 * w) = ax[w];
                         }
                     }
                 }
+#ifdef OZ_DBG_NO_STORE
+                if (interior) {
+                    if ((pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]) == 0x12345u) *reinterpret_cast<uint32_t *>(po) = pk[0];
+                } else {
+#else
+                if (interior && vec32_ok) {
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(po), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                                 "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                } else if (interior) {
+                    *reinterpret_cast<uint4 *>(po)      = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4 *>(po + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else {
+#endif
+#pragma unroll
+                    for (int w = 0; w < 8; ++w)
+                        if (row0 + 32 * c + 4 * w < args.rows_store) *reinterpret_cast<uint32_t *>(po + 4 * w) = pk[w];
+                }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(tempty_bar(acc), 0));   // tell the leader: this warp has drained the buffer
         }
     }
 
@@ -797,21 +844,29 @@ bool pair_kernel_enabled(cudaStream_t st) {
 template <bool RMW>
 cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     CUtensorMap ma, mb;
-    if (!make_operand_map(&ma, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, 128)) return cudaErrorInvalidValue;
-    if (!make_operand_map(&mb, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, 128)) return cudaErrorInvalidValue;
+    // swapped roles (see the epilogue): the MMA's M side walks rows of B8i = columns of C, its N side rows of A8i = rows of C
+    if (!make_operand_map(&ma, p.B8i, p.ld8i, p.rowsB, p.num_slices, p.sizeB, 128)) return cudaErrorInvalidValue;
+    if (!make_operand_map(&mb, p.A8i, p.ld8i, p.rowsA, p.num_slices, p.sizeA, 128)) return cudaErrorInvalidValue;
     const Tuning tn = tuning();
     PairArgs a{};
     a.rowsA = (uint32_t)p.rowsA; a.rowsB = (uint32_t)p.rowsB;
     a.num_kb = (uint32_t)((p.ld8i + BLOCK_K - 1) / BLOCK_K);
     a.first_modulus = p.first_modulus;
     a.rows_store = (uint32_t)((p.rowsA + 3) / 4 * 4);
-    a.sched.init((uint32_t)((p.rowsA + 255) / 256), (uint32_t)((p.rowsB + BLOCK_N - 1) / BLOCK_N), p.num_slices,
-                 tn.pair_band > 0 ? (uint32_t)tn.pair_band : (uint32_t)PAIR_BAND);
+    // Band: the column tiles of C whose B8i rows, for one modulus, the pairs walk together.  Its slice rows (band x 256 x ld8i
+    // bytes) should stay in L2 while all row tiles pass: ~32 MB measured best from k = 512 to 16384 (band 64 ... 8 at
+    // 16384^2 x k; profiles/r02_ab_band.jsonl).  Option pair_band > 0 overrides.
+    uint32_t band = (uint32_t)tn.pair_band;
+    if (tn.pair_band <= 0) {
+        const size_t fit = ((size_t)32 << 20) / (256 * p.ld8i);
+        band = (uint32_t)(fit < 4 ? 4 : fit > 4096 ? 4096 : fit);
+    }
+    a.sched.init((uint32_t)((p.rowsB + 255) / 256), (uint32_t)((p.rowsA + BLOCK_N - 1) / BLOCK_N), p.num_slices, band);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
     a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
-    const int stages = tn.pair_stages ? tn.pair_stages : p.share_sm ? 4 : PAIR_STAGES;
-    auto kern = stages == 4 ? oz_gemm_pair_kernel<RMW, 4> : stages == 5 ? oz_gemm_pair_kernel<RMW, 5> : oz_gemm_pair_kernel<RMW, 6>;
-    const int smem_bytes = pair_smem_total(stages == 4 ? 4 : stages == 5 ? 5 : 6);
+    const int stages = tn.pair_stages ? tn.pair_stages : p.share_sm ? 4 : PAIR_STAGES;   // (7 fit too: no measurable difference)
+    auto kern = stages == 4 ? oz_gemm_pair_kernel<RMW, 4> : stages == 5 ? oz_gemm_pair_kernel<RMW, 5> : stages == 7 ? oz_gemm_pair_kernel<RMW, 7> : oz_gemm_pair_kernel<RMW, 6>;
+    const int smem_bytes = pair_smem_total(stages == 4 ? 4 : stages == 5 ? 5 : stages == 7 ? 7 : 6);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const uint32_t max_pairs = (uint32_t)sm_count() / 2;

@@ -184,9 +184,8 @@ oz_gemm_crt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (uint32_t j = 0; j < N; ++j, ++it) {
                 const uint32_t acc = it % FT_ACC, acc_phase = (it / FT_ACC) & 1;
                 const uint32_t taddr = tmem_base + acc * FT_ACC_STRIDE + ((uint32_t)(q * 32) << 16) + half * FT_COLS;
-                const uint32_t m   = (uint32_t)dev_tab::OZ_MOD[j];
-                const uint32_t inv = (uint32_t)(4294967296ull / m);
-                const uint32_t off = m * ((kMaxAbsProduct + m - 1) / m);
+                const uint32_t inv = dev_tab::OZ_BARRETT_INV[j], negm = dev_tab::OZ_BARRETT_NEGM[j];
+                const uint32_t off = dev_tab::OZ_BARRETT_OFF[j];
                 double w1, w2 = 0.0;
                 if constexpr (SPLIT) { w1 = dev_tab::OZ_W2_HI[N - 8][j]; w2 = dev_tab::OZ_W2_LO[N - 8][j]; }
                 else                 { w1 = dev_tab::OZ_W1[ti_w][j]; }
@@ -208,7 +207,7 @@ oz_gemm_crt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         for (int e = 0; e < 16; ++e) v[e] &= 0xffu;
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = reduce_mod_u((int32_t)v[e], m, inv, off);
+                        for (int e = 0; e < 16; ++e) v[e] = reduce_mod_u((int32_t)v[e], negm, inv, off);
                     }
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
