@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the 65536^3 sub-record (N = 1: low-memory call; N >= 4: --strong)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity checks after the timed region")
+    ap.add_argument("--exchange", default="copy", choices=["copy", "nccl", "python"],
+                    help="N > 1: the C ABI entry gemmul8_b200_pgemm with copy engines over peer memory (default; falls back to NCCL if "
+                         "CUDA IPC is unavailable) or with NCCL collectives; 'python' = round 1's torch.distributed orchestration")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: ONE m = n = k = --size problem block-partitioned over the P x Q grid (BASELINE config 5: --size 65536) "
                          "instead of the default weak scaling (one --size^2 block of C per GPU)")
@@ -298,11 +301,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    grid = None
+    grid, mpgrid, exchange_text = None, None, "torch.distributed (NCCL all-gather of FP64 panels), Python orchestration"
     if multi:
         from importlib import import_module
         dmod = import_module("gemmul8_b200.distributed")
         grid = dmod.BlockGrid()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import dist_check
+
+    def open_mp_grid(m, n, k):
+        """The C++ grid (include/gemmul8_b200_mp.h) sized for this problem's panels."""
+        nonlocal mpgrid, exchange_text
+        if mpgrid is not None:
+            mpgrid.close()
+            mpgrid = None
+        if args.exchange != "python":
+            mpgrid, exchange_text = dist_check.make_mp_grid(grid, 8 * (m // grid.P) * k, 8 * k * (n // grid.Q), args.exchange)
 
     def multi_problem(m, n, k):
         """Operands and the step of one partitioned problem: every rank generates only the pieces it owns."""
@@ -314,8 +328,11 @@ def main():
         work = torch.empty(g.workSize(m_loc, n_loc, k, N), dtype=torch.uint8, device="cuda")
         Cm = torch.zeros((n_loc, m_loc), dtype=torch.float64, device="cuda")
 
+        open_mp_grid(m, n, k)
+        pg = dist_check.cpp_pgemm(mpgrid) if mpgrid is not None else dmod.pgemm
+
         def step(flags=0):
-            return dmod.pgemm(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, Cm, N, fast, work, flags=flags)
+            return pg(grid, g, m, n, k, 1.0, a_slice, b_slice, 0.0, Cm, N, fast, work, flags=flags)
         return step, m_loc, n_loc, (a_slice, b_slice, work, Cm)
 
     if multi:
@@ -382,7 +399,7 @@ def main():
     gemm_ms = phase[1] / psteps / 1e6
     scal_ms = phase[0] / psteps / 1e6
     crt_ms = phase[3] / psteps / 1e6
-    grid_text = f", {grid.P}x{grid.Q} C-block grid, NCCL all-gather of FP64 panels" if multi else ""
+    grid_text = f", {grid.P}x{grid.Q} C-block grid, panel exchange: {exchange_text}" if multi else ""
     out["config"] = config_of(m, n, k, N, fast, world, grid_text)
 
     if rank == 0 and not multi:
@@ -494,8 +511,6 @@ def main():
 
     # ---- N > 1: parity of the partitioned path (outside the timed region), then BASELINE config 5 ----
     if multi and not args.no_parity:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import dist_check
         try:
             # the block of C the timed steps left behind, against a double-double product of the gathered panels
             a_panel = grid.gather_a_panel(keep[0], m_loc, k)
@@ -505,9 +520,10 @@ def main():
             T1, T2 = g.dd_gemm(m_loc, n_loc, k, a_panel, m_loc, b_panel, k, rows=rows, cols=cols)
             err = allmax((((Cm[cols.long()][:, rows.long()] - T1) - T2) / T1).abs().max().item())
             del a_panel, b_panel, T1, T2
-            par = dist_check.run_checks(grid, dmod, 1024, verbose=False)
+            par = dist_check.run_checks(grid, dmod, 1024, verbose=False, pgemm=dist_check.cpp_pgemm(mpgrid) if mpgrid is not None else None)
             par["timed_result_relerr_max_vs_dd"] = err
             par["ok"] = bool(par["ok"] and err < (1e-6 if N >= 14 else 1e-2))
+            par["entry"] = "gemmul8_b200_pgemm (C ABI)" if mpgrid is not None else "distributed.pgemm (Python)"
             par["what"] = ("tools/dist_check.run_checks on every rank: pipelined exchange == plain exchange bit for bit, sampled double-double "
                            "truth, accurate-mode block == block of the unpartitioned accurate product bit for bit; plus the timed run's own C "
                            "block against a sampled double-double truth (max over ranks)")
@@ -529,6 +545,7 @@ def main():
                               "steps": 2, "warmup": 1, "ms_per_step": ms5, "value": 2.0 * S5 ** 3 / (ms5 * 1e-3) / 1e12, "unit": "TFLOPS",
                               "phases_ms_rank0": {"scaling": ph5[0] / 2e6, "int8_gemm_fused_residue": ph5[1] / 2e6, "crt_inverse_scaling": ph5[3] / 2e6},
                               "note": "BASELINE config 5; parallel efficiency = (1-GPU config5.ms_per_step of the N=1 line) / (n_gpus * this ms_per_step)"}
+            out["config5"]["exchange"] = exchange_text
             del keep5, step5
         except Exception as e:
             out["config5"] = {"error": str(e)[:300]}
@@ -567,6 +584,8 @@ def main():
                 out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out), flush=True)
     if multi:
+        if mpgrid is not None:
+            mpgrid.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0

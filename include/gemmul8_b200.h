@@ -69,6 +69,8 @@ enum {
     GEMMUL8_FLAG_DEVICE_SCALARS = 1u << 16, /* alpha and beta point to DEVICE memory (CUBLAS_POINTER_MODE_DEVICE callers): they are read by
                                                the CRT kernel, never on the host (the reference dereferences on the host,
                                                GEMMul8/src/gemmul8.cu:288).  Not for gemm_host.                                  */
+    GEMMUL8_FLAG_EXCLUSIVE_SMS  = 1u << 17, /* gemm_part: nothing else needs room on the SMs beside the product (e.g. the panel exchange runs
+                                               on copy engines): full pipeline depth instead of the 4 stages that leave room for NCCL's kernels */
     GEMMUL8_FLAG_PHASE_LOG      = 1u << 13  /* record the phase boundaries as events WITHOUT synchronising; the times of all such
                                                calls of this host thread are summed by gemmul8_b200_phase_log_collect()      */
 };

@@ -25,7 +25,7 @@ F32, F64, C32, C64 = 0, 1, 2, 3
 FLAG_TIMERS, FLAG_STAGE_SCALING, FLAG_STAGE_RESIDUES, FLAG_FUSED_CRT, FLAG_GEMM_SIMT, FLAG_HOST_SERIAL, FLAG_STRIPS = 1, 1 << 4, 1 << 5, 1 << 6, 1 << 8, 1 << 9, 1 << 10
 FLAG_ONLY_SCALE_A, FLAG_SKIP_SCALE_A, FLAG_PHASE_LOG = 1 << 11, 1 << 12, 1 << 13
 FLAG_ONLY_BOUND, FLAG_SKIP_BOUND = 1 << 14, 1 << 15
-FLAG_DEVICE_SCALARS = 1 << 16
+FLAG_DEVICE_SCALARS, FLAG_EXCLUSIVE_SMS = 1 << 16, 1 << 17
 
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",

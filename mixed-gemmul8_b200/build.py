@@ -2,6 +2,8 @@
 
   libgemmul8_b200.so        product: C ABI (include/gemmul8_b200.h), kernels, no cuBLAS dependency
   libgemmul8_b200_blas.so   LD_PRELOAD interposer: cublasDgemm / Sgemm / Zgemm / Cgemm / GemmEx -> the product library
+  libgemmul8_b200_mp.so     multi-GPU layer (include/gemmul8_b200_mp.h): 2-D block decomposition, panel exchange over NCCL or
+                            copy engines; links NCCL, not part of the single-GPU product library
   libgemmul8_b200_aux.so    measurement helpers used by tests / bench only (phi-matrix generator,
                             double-double truth GEMM, cuBLAS native baselines)
 """
@@ -15,6 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgemmul8_b200.so")
 AUX = os.path.join(HERE, "libgemmul8_b200_aux.so")
 BLAS = os.path.join(HERE, "libgemmul8_b200_blas.so")
+MP = os.path.join(HERE, "libgemmul8_b200_mp.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -55,6 +58,12 @@ def build(force=False, verbose=False):
         cuda = os.path.dirname(os.path.dirname(nvcc()))
         out += _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(cuda, "include"), "-o", BLAS, blas_src,
                      "-L", HERE, "-lgemmul8_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-ldl", "-Wl,-rpath,$ORIGIN"])
+    mp_src = os.path.join(CSRC, "oz_mp.cpp")
+    if os.path.exists(mp_src) and (force or _stale(MP, [mp_src, LIB, os.path.join(HERE, "..", "include", "gemmul8_b200_mp.h")])):
+        # host code only: panel exchange (NCCL or copy engines over CUDA IPC) around the block-wise entry of the product library
+        cuda = os.path.dirname(os.path.dirname(nvcc()))
+        out += _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(cuda, "include"), "-o", MP, mp_src,
+                     "-L", HERE, "-lgemmul8_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lnccl", "-ldl", "-Wl,-rpath,$ORIGIN"])
     aux_src = os.path.join(CSRC, "oz_aux.cu")
     if os.path.exists(aux_src) and (force or _stale(AUX, [aux_src])):
         out += _run([nvcc(), *ARCH, *COMMON, "-shared", "-o", AUX, aux_src, "-lcublas"])

@@ -599,8 +599,10 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
     int rc = check_args(a);
     if (rc) return rc;
     if (is_complex(a->dtype_C) || !a->fastmode) return fail(GEMMUL8_ERR_ARGUMENT, "gemm_part: real types in fast mode only");
-    if (row1 > a->m || col1 > a->n || row0 > row1 || col0 > col1 || (row0 % 256) || (col0 % 256))
-        return fail(GEMMUL8_ERR_ARGUMENT, "gemm_part: bad block (row0 / col0 must be multiples of 256 inside the matrix)");
+    // whole GEMM tiles for a product; the scaling steps work per row / column and take any range
+    const bool tile_aligned = !(parts & GEMMUL8_PART_PRODUCT) || ((row0 % 256) == 0 && (col0 % 256) == 0);
+    if (row1 > a->m || col1 > a->n || row0 > row1 || col0 > col1 || !tile_aligned)
+        return fail(GEMMUL8_ERR_ARGUMENT, "gemm_part: bad block (row0 / col0 of a product must be multiples of 256 inside the matrix)");
     const size_t m = a->m, n = a->n, k = a->k;
     const unsigned N = a->num_moduli, ti = N - 2;
     cudaStream_t st = static_cast<cudaStream_t>(a->stream);
@@ -642,7 +644,7 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *a, int parts, size_t row0, size_t 
         gp.A8i = A8i + row0 * L.lda8i; gp.rowsA = row1 - row0;
         gp.B8i = B8i + col0 * L.lda8i; gp.rowsB = col1 - col0;
         gp.C8u = C8u + col0 * L.m_pad + row0;
-        gp.share_sm = true;   // a block-wise caller overlaps this product with transfers of the next pieces
+        gp.share_sm = (a->flags & GEMMUL8_FLAG_EXCLUSIVE_SMS) == 0;   // a block-wise caller usually overlaps this product with NCCL transfers
         timer.mark();
         rc = block_to_c(a, gp, take_fused(a), split, static_cast<uint8_t *>(a->C) + (col0 * a->ldc + row0) * esC, sftA + row0, sftB + col0, st, &timer);
         if (rc) return rc;

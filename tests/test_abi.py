@@ -171,3 +171,26 @@ def test_options_api_without_a_device(g):
     if not torch.cuda.is_available():
         with pytest.raises(g.Gemmul8Error):
             g.init()
+
+
+def test_multi_gpu_abi_symbols_and_row_pieces(g):
+    """include/gemmul8_b200_mp.h: every declared entry point is exported by libgemmul8_b200_mp.so; the row-piece partition of
+    an A panel (host logic of gemmul8_b200_pgemm) covers the block on tile boundaries."""
+    from importlib import import_module
+    mp = import_module("gemmul8_b200.mp")
+    header = open(os.path.join(ROOT, "include", "gemmul8_b200_mp.h")).read()
+    declared = set(re.findall(r"\b(gemmul8_b200_\w+)\s*\(", header))
+    lib = mp.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/gemmul8_b200_mp.h but not exported"
+    assert declared == set(mp.EXPORTED_SYMBOLS)
+    for rows in (1, 255, 256, 257, 300, 777, 1000, 4096, 16384, 32768, 33000):
+        for want in (1, 2, 4, 8):
+            pcs = mp.row_pieces(rows, want)
+            assert pcs[0][0] == 0 and pcs[-1][1] == rows and len(pcs) <= want
+            assert all(a[1] == b[0] for a, b in zip(pcs, pcs[1:]))
+            assert all(r0 % 256 == 0 and r1 > r0 for r0, r1 in pcs)
+    # the product library itself stays free of NCCL (the multi-GPU layer is a separate library)
+    import subprocess
+    out = subprocess.run(["ldd", g.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "nccl" not in out.lower()

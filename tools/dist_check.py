@@ -76,19 +76,62 @@ def run_checks(grid, dmod, S=2048, verbose=True, pgemm=None):
     return {"ok": flag.item() == 0, "ranks": dist.get_world_size(), "cases_rank0": details}
 
 
+def cpp_pgemm(mpgrid):
+    """distributed.pgemm's signature on top of the C ABI (gemmul8_b200_pgemm): what bench.py times for N > 1."""
+    def f(grid, pkg, m, n, k, alpha, a_slice, b_slice, beta, Cm, N, fast, work, flags=0):
+        m_loc = m // grid.P
+        return mpgrid.pgemm(m, n, k, alpha, a_slice, m_loc, b_slice, k, beta, Cm, m_loc, N, fast, work, flags)
+    return f
+
+
+def make_mp_grid(grid, a_bytes, b_bytes, want="copy"):
+    """The C++ grid with the copy-engine exchange, or (if CUDA IPC / peer access is unavailable, or asked for) NCCL."""
+    mp = import_module("gemmul8_b200.mp")
+    if want == "copy":
+        ok = torch.tensor([1], device="cuda")
+        try:
+            mg = mp.Grid(grid.P, grid.Q, a_bytes, b_bytes, mp.EXCHANGE_COPY)
+        except Exception as e:       # every rank must take the same decision
+            mg, ok[0] = None, 0
+            print(f"rank {dist.get_rank()}: copy-engine exchange unavailable ({e})", flush=True)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 1:
+            return mg, "copy engines over CUDA IPC peer memory (cudaMemcpy2DAsync pushes + stream memory-op flags)"
+        if mg is not None:
+            mg.close()
+    return mp.Grid(grid.P, grid.Q, a_bytes, b_bytes, mp.EXCHANGE_NCCL), "NCCL all-gather / broadcast of FP64 panel pieces"
+
+
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    which = sys.argv[2] if len(sys.argv) > 2 else "all"        # python | nccl | copy | all
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dmod = import_module("gemmul8_b200.distributed")
     grid = dmod.BlockGrid()
-    res = run_checks(grid, dmod, S)
+    ok = True
+    for name in (["python", "nccl", "copy"] if which == "all" else [which]):
+        if name == "python":
+            res = run_checks(grid, dmod, S)
+        else:
+            cap = 8 * max(S * S, 1280 * 4 * 640, 4 * 640 * 768)
+            mg, how = make_mp_grid(grid, cap, cap, name)
+            res = run_checks(grid, dmod, S, pgemm=cpp_pgemm(mg))
+            # the same grid again: epochs, acknowledgements and buffer reuse across calls
+            res2 = run_checks(grid, dmod, S // 2, verbose=False, pgemm=cpp_pgemm(mg))
+            res["ok"] = res["ok"] and res2["ok"]
+            mg.close()
+            if dist.get_rank() == 0:
+                print(f"C ABI pgemm, exchange: {how}", flush=True)
+        if dist.get_rank() == 0:
+            print(f"DIST {name}: " + ("OK" if res["ok"] else "FAILED"), flush=True)
+        ok = ok and res["ok"]
     if dist.get_rank() == 0:
-        print("DIST OK" if res["ok"] else "DIST FAILED", flush=True)
+        print("DIST OK" if ok else "DIST FAILED", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    return 0 if res["ok"] else 1
+    return 0 if ok else 1
 
 
 if __name__ == "__main__":
