@@ -77,8 +77,11 @@ struct gemmul8_b200_grid {
     int rank = 0, nranks = 1, P = 1, Q = 1, p = 0, q = 0, device = 0, exchange = 0;
     ncclComm_t world = nullptr, row = nullptr, col = nullptr;
     bool own_world = false;
-    cudaStream_t xa = nullptr, xb = nullptr;
+    cudaStream_t xa = nullptr, xb = nullptr;             // NCCL transport / local copies: one stream per direction
+    cudaStream_t xpa[kMaxSide] = {}, xpb[kMaxSide] = {}; // COPY transport: one stream per peer, so that the pushes to different
+                                                         // peers run on different copy engines at the same time
     cudaEvent_t ev_start = nullptr, ev_a[kMaxPieces] = {}, ev_b[kMaxSide] = {}, ev_xa_done = nullptr, ev_xb_done = nullptr;
+    cudaEvent_t ev_pa[kMaxSide] = {}, ev_pb[kMaxSide] = {};
     uint8_t *a_buf = nullptr, *b_buf = nullptr;
     size_t a_cap = 0, b_cap = 0;
     // COPY transport
@@ -163,6 +166,16 @@ int finish_create(gemmul8_b200_grid *g, size_t a_bytes, size_t b_bytes) {
         // a rank that shares both my row and my column is me; otherwise the flag array of a column peer is a second mapping
         MP_CUDA(open(all[r].f, reinterpret_cast<void **>(&g->peer_flags_col[pp])), "ipc open flags");
     }
+    for (int qq = 0; qq < g->Q; ++qq)
+        if (qq != g->q) {
+            MP_CUDA(cudaStreamCreateWithFlags(&g->xpa[qq], cudaStreamNonBlocking), "stream");
+            MP_CUDA(cudaEventCreateWithFlags(&g->ev_pa[qq], cudaEventDisableTiming), "event");
+        }
+    for (int pp = 0; pp < g->P; ++pp)
+        if (pp != g->p) {
+            MP_CUDA(cudaStreamCreateWithFlags(&g->xpb[pp], cudaStreamNonBlocking), "stream");
+            MP_CUDA(cudaEventCreateWithFlags(&g->ev_pb[pp], cudaEventDisableTiming), "event");
+        }
     // (flags were zeroed before their handle was published, so no peer can push before that)
     return GEMMUL8_OK;
 }
@@ -265,6 +278,10 @@ int gemmul8_b200_grid_destroy(gemmul8_b200_grid *g) {
     if (g->ev_start) cudaEventDestroy(g->ev_start);
     if (g->ev_xa_done) cudaEventDestroy(g->ev_xa_done);
     if (g->ev_xb_done) cudaEventDestroy(g->ev_xb_done);
+    for (auto s : g->xpa) if (s) cudaStreamDestroy(s);
+    for (auto s : g->xpb) if (s) cudaStreamDestroy(s);
+    for (auto e : g->ev_pa) if (e) cudaEventDestroy(e);
+    for (auto e : g->ev_pb) if (e) cudaEventDestroy(e);
     if (g->xa) cudaStreamDestroy(g->xa);
     if (g->xb) cudaStreamDestroy(g->xb);
     cudaGetLastError();
@@ -313,9 +330,20 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     ga.dtype_A = a->dtype_A; ga.dtype_B = a->dtype_B; ga.dtype_C = a->dtype_C;
     ga.stream = a->stream; ga.flags = a->flags | (copy ? (unsigned)GEMMUL8_FLAG_EXCLUSIVE_SMS : 0u);
 
+    // Row pieces of the A panel.  NCCL: four equal pieces (each gather is a kernel that competes with the product before it).
+    // COPY: a small first piece (1/8 of the rows, whole tiles) whose products cover the arrival of everything else, then the
+    // rest in one piece: fewer, larger scaling and product launches (measured: 4 equal pieces cost ~2 ms of extra scaling time).
     size_t rb[9];
-    const int npieces = (Q > 1 && pipelined) ? row_pieces(m_loc, kMaxPieces, rb) : 1;
-    if (npieces == 1) { rb[0] = 0; rb[1] = m_loc; }
+    int npieces = 1;
+    rb[0] = 0; rb[1] = m_loc;
+    if (Q > 1 && pipelined) {
+        if (copy) {
+            const size_t first = ((m_loc / 8 + 255) / 256) * 256;
+            if (first > 0 && first < m_loc) { rb[1] = first; rb[2] = m_loc; npieces = 2; }
+        } else {
+            npieces = row_pieces(m_loc, kMaxPieces, rb);
+        }
+    }
 
     // ---------------- exchange ----------------
     // The side streams start behind everything already queued on the compute stream: the caller's producers of a_slice /
@@ -324,25 +352,29 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     if (Q > 1) {
         MP_CUDA(cudaStreamWaitEvent(g->xa, g->ev_start, 0), "stream wait");
         const uint8_t *src = static_cast<const uint8_t *>(a->a_slice);
-        if (copy && epoch > 1)   // peers must have finished reading what I pushed last time
-            for (size_t qq = 0; qq < Q; ++qq)
-                if ((int)qq != g->q) { int rc = wait_flag(g->flags, gemmul8_b200_grid::F_ACK_A + (int)qq, epoch - 1, g->xa); if (rc) return rc; }
-        for (int i = 0; i < npieces; ++i) {
-            const size_t r0 = rb[i], rows = rb[i + 1] - rb[i];
-            // piece i is its own column-major rows x k matrix at byte offset r0 * k * es; my k/Q columns sit at column q * k/Q
-            const size_t off = (r0 * k + (size_t)g->q * kq * rows) * esA;
-            if (copy) {
-                for (size_t d = 0; d < Q; ++d) {        // own buffer first, then the peers, starting with the right neighbour
-                    const size_t qq = ((size_t)g->q + d) % Q;
-                    MP_CUDA(cudaMemcpy2DAsync(g->peer_a[qq] + off, rows * esA, src + r0 * esA, a->lda * esA, rows * esA, kq, cudaMemcpyDeviceToDevice, g->xa), "push A piece");
-                    if ((int)qq != g->q) { int rc = raise_flag(g->peer_flags_row[qq], gemmul8_b200_grid::F_A + i * kMaxSide + g->q, epoch, g->xa); if (rc) return rc; }
-                    else MP_CUDA(cudaEventRecord(g->ev_a[i], g->xa), "event record");     // my own part is in place
+        // piece i is its own column-major rows x k matrix at byte offset r0 * k * es; my k/Q columns sit at column q * k/Q
+        auto piece_off = [&](int i) { return (rb[i] * k + (size_t)g->q * kq * (rb[i + 1] - rb[i])) * esA; };
+        if (copy) {
+            // remote pushes: one stream per peer (right neighbour first), all pieces in order, a flag behind each
+            for (size_t d = 1; d < Q; ++d) {
+                const size_t qq = ((size_t)g->q + d) % Q;
+                cudaStream_t xs = g->xpa[qq];
+                MP_CUDA(cudaStreamWaitEvent(xs, g->ev_start, 0), "stream wait");
+                if (epoch > 1) { int rc = wait_flag(g->flags, gemmul8_b200_grid::F_ACK_A + (int)qq, epoch - 1, xs); if (rc) return rc; }   // the peer has read what I pushed last time
+                for (int i = 0; i < npieces; ++i) {
+                    const size_t rows = rb[i + 1] - rb[i];
+                    MP_CUDA(cudaMemcpy2DAsync(g->peer_a[qq] + piece_off(i), rows * esA, src + rb[i] * esA, a->lda * esA, rows * esA, kq, cudaMemcpyDeviceToDevice, xs), "push A piece");
+                    int rc = raise_flag(g->peer_flags_row[qq], gemmul8_b200_grid::F_A + i * kMaxSide + g->q, epoch, xs);
+                    if (rc) return rc;
                 }
-                continue;
-            } else {
-                MP_CUDA(cudaMemcpy2DAsync(g->a_buf + off, rows * esA, src + r0 * esA, a->lda * esA, rows * esA, kq, cudaMemcpyDeviceToDevice, g->xa), "pack A piece");
-                MP_NCCL(ncclAllGather(g->a_buf + off, g->a_buf + r0 * k * esA, rows * kq * esA, ncclInt8, g->row, g->xa), "all-gather A piece");
+                MP_CUDA(cudaEventRecord(g->ev_pa[qq], xs), "event record");
             }
+        }
+        for (int i = 0; i < npieces; ++i) {
+            const size_t rows = rb[i + 1] - rb[i];
+            // my own part goes into my own buffer (both transports); NCCL then gathers the piece in place
+            MP_CUDA(cudaMemcpy2DAsync(g->a_buf + piece_off(i), rows * esA, src + rb[i] * esA, a->lda * esA, rows * esA, kq, cudaMemcpyDeviceToDevice, g->xa), "own part of A piece");
+            if (!copy) MP_NCCL(ncclAllGather(g->a_buf + piece_off(i), g->a_buf + rb[i] * k * esA, rows * kq * esA, ncclInt8, g->row, g->xa), "all-gather A piece");
             MP_CUDA(cudaEventRecord(g->ev_a[i], g->xa), "event record");
         }
     }
@@ -351,17 +383,21 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
         const uint8_t *src = static_cast<const uint8_t *>(a->b_slice);
         const size_t off = (size_t)g->p * w * k * esB;       // my w columns of the k x n_loc panel
         if (copy) {
-            if (epoch > 1)
-                for (size_t pp = 0; pp < P; ++pp)
-                    if ((int)pp != g->p) { int rc = wait_flag(g->flags, gemmul8_b200_grid::F_ACK_B + (int)pp, epoch - 1, g->xb); if (rc) return rc; }
-            for (size_t d = 0; d < P; ++d) {
+            for (size_t d = 1; d < P; ++d) {
                 const size_t pp = ((size_t)g->p + d) % P;
-                MP_CUDA(cudaMemcpy2DAsync(g->peer_b[pp] + off, k * esB, src, a->ldb * esB, k * esB, w, cudaMemcpyDeviceToDevice, g->xb), "push B block");
-                if ((int)pp != g->p) { int rc = raise_flag(g->peer_flags_col[pp], gemmul8_b200_grid::F_B + g->p, epoch, g->xb); if (rc) return rc; }
-                if ((int)pp == g->p) MP_CUDA(cudaEventRecord(g->ev_b[g->p], g->xb), "event record");
+                cudaStream_t xs = g->xpb[pp];
+                MP_CUDA(cudaStreamWaitEvent(xs, g->ev_start, 0), "stream wait");
+                if (epoch > 1) { int rc = wait_flag(g->flags, gemmul8_b200_grid::F_ACK_B + (int)pp, epoch - 1, xs); if (rc) return rc; }
+                MP_CUDA(cudaMemcpy2DAsync(g->peer_b[pp] + off, k * esB, src, a->ldb * esB, k * esB, w, cudaMemcpyDeviceToDevice, xs), "push B block");
+                int rc = raise_flag(g->peer_flags_col[pp], gemmul8_b200_grid::F_B + g->p, epoch, xs);
+                if (rc) return rc;
+                MP_CUDA(cudaEventRecord(g->ev_pb[pp], xs), "event record");
             }
+        }
+        MP_CUDA(cudaMemcpy2DAsync(g->b_buf + off, k * esB, src, a->ldb * esB, k * esB, w, cudaMemcpyDeviceToDevice, g->xb), "own B block");
+        if (copy) {
+            MP_CUDA(cudaEventRecord(g->ev_b[g->p], g->xb), "event record");
         } else {
-            MP_CUDA(cudaMemcpy2DAsync(g->b_buf + off, k * esB, src, a->ldb * esB, k * esB, w, cudaMemcpyDeviceToDevice, g->xb), "pack B block");
             for (size_t pp = 0; pp < P; ++pp) {
                 uint8_t *blk = g->b_buf + pp * w * k * esB;
                 MP_NCCL(ncclBroadcast(blk, blk, w * k * esB, ncclInt8, (int)pp, g->col, g->xb), "broadcast B block");
@@ -402,6 +438,19 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     int rc;
     if (pipelined) {
         // ---------------- fast mode: block-wise, products start while later pieces are in flight ----------------
+        bool acked = false;
+        int a_scaled = 0;
+        size_t b_scaled = 0;
+        auto maybe_ack = [&]() -> int {     // once every operand has been encoded the panel buffers are free: tell the producers
+            if (acked || a_scaled < npieces || b_scaled < P) return GEMMUL8_OK;
+            acked = true;
+            return ack();
+        };
+        auto part = [&](gemmul8_b200_args &pa, int what, size_t r0, size_t r1, size_t c0, size_t c1, const char *name) -> int {
+            int rc2 = check(gemmul8_b200_gemm_part(&pa, what, r0, r1, c0, c1), name);
+            for (int t = 0; t < 4; ++t) a->timers_ns[t] += pa.timers_ns[t];
+            return rc2;
+        };
         for (int i = 0; i < npieces; ++i) {
             const size_t r0 = rb[i], r1 = rb[i + 1];
             gemmul8_b200_args pa = ga;
@@ -410,21 +459,28 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
                 pa.A   = g->a_buf + r0 * k * esA - r0 * esA;
             }
             if ((rc = a_ready(i))) return rc;
-            if ((rc = check(gemmul8_b200_gemm_part(&pa, GEMMUL8_PART_SCALE_A, r0, r1, 0, 0), "scale A piece"))) return rc;
-            for (int t = 0; t < 4; ++t) a->timers_ns[t] += pa.timers_ns[t];
-            if (i == 0) {
-                for (size_t d = 0; d < P; ++d) {
-                    const size_t pp = ((size_t)g->p + d) % P;        // own block first: it needs no transfer
-                    if ((rc = b_ready(pp))) return rc;
-                    const size_t c0 = P > 1 ? pp * w : 0, c1 = P > 1 ? (pp + 1) * w : n_loc;
-                    // (column blocks need not start on a tile boundary for SCALE_B: its kernels work per column)
-                    if ((rc = check(gemmul8_b200_gemm_part(&pa, GEMMUL8_PART_SCALE_B, 0, 0, c0, c1), "scale B block"))) return rc;
-                    for (int t = 0; t < 4; ++t) a->timers_ns[t] += pa.timers_ns[t];
-                }
+            if ((rc = part(pa, GEMMUL8_PART_SCALE_A, r0, r1, 0, 0, "scale A piece"))) return rc;
+            ++a_scaled;
+            if (i > 0) {
+                if ((rc = maybe_ack())) return rc;
+                if ((rc = part(pa, GEMMUL8_PART_PRODUCT, r0, r1, 0, n_loc, "product"))) return rc;
+                continue;
             }
-            if (i == npieces - 1 && (rc = ack())) return rc;          // every operand has been encoded: the panel buffers are free
-            if ((rc = check(gemmul8_b200_gemm_part(&pa, GEMMUL8_PART_PRODUCT, r0, r1, 0, n_loc), "product"))) return rc;
-            for (int t = 0; t < 4; ++t) a->timers_ns[t] += pa.timers_ns[t];
+            // First piece: B arrives block by block, the own block first (it needs no transfer).  The product of this piece is
+            // issued per B block as soon as that block is encoded, so the tensor cores start after one piece of A and 1/P of B
+            // instead of after the whole B panel.  (Column blocks need not start on a tile boundary for SCALE_B, whose kernels
+            // work per column; a product does.)
+            const bool per_block = P > 1 && (w % 256) == 0;
+            for (size_t d = 0; d < P; ++d) {
+                const size_t pp = ((size_t)g->p + d) % P;
+                if ((rc = b_ready(pp))) return rc;
+                const size_t c0 = P > 1 ? pp * w : 0, c1 = P > 1 ? (pp + 1) * w : n_loc;
+                if ((rc = part(pa, GEMMUL8_PART_SCALE_B, 0, 0, c0, c1, "scale B block"))) return rc;
+                ++b_scaled;
+                if ((rc = maybe_ack())) return rc;
+                if (per_block && (rc = part(pa, GEMMUL8_PART_PRODUCT, r0, r1, c0, c1, "product"))) return rc;
+            }
+            if (!per_block && (rc = part(pa, GEMMUL8_PART_PRODUCT, r0, r1, 0, n_loc, "product"))) return rc;
         }
     } else {
         // ---------------- accurate mode (and k == 0): whole panels, then the call split at the bound product ----------------
@@ -456,6 +512,10 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     // the exchange streams' work of this call is part of the call: a later operation on `st` is ordered behind it
     if (Q > 1) { MP_CUDA(cudaEventRecord(g->ev_xa_done, g->xa), "event record"); MP_CUDA(cudaStreamWaitEvent(st, g->ev_xa_done, 0), "stream wait"); }
     if (P > 1) { MP_CUDA(cudaEventRecord(g->ev_xb_done, g->xb), "event record"); MP_CUDA(cudaStreamWaitEvent(st, g->ev_xb_done, 0), "stream wait"); }
+    if (copy) {   // ... including my pushes to the peers (the caller may overwrite a_slice / b_slice behind this call)
+        for (size_t qq = 0; qq < Q; ++qq) if ((int)qq != g->q && Q > 1) MP_CUDA(cudaStreamWaitEvent(st, g->ev_pa[qq], 0), "stream wait");
+        for (size_t pp = 0; pp < P; ++pp) if ((int)pp != g->p && P > 1) MP_CUDA(cudaStreamWaitEvent(st, g->ev_pb[pp], 0), "stream wait");
+    }
     return GEMMUL8_OK;
 }
 

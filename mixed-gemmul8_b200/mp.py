@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-MP_PATH = os.path.join(_HERE, "libgemmul8_b200_mp.so")
+MP_PATH = os.environ.get("GEMMUL8_B200_MP_LIB") or os.path.join(_HERE, "libgemmul8_b200_mp.so")   # (override: A/B timing of builds)
 EXCHANGE_NCCL, EXCHANGE_COPY = 0, 1
 ID_BYTES = 128
 

@@ -1,0 +1,17 @@
+#!/bin/bash
+# N GPUs: correctness of all three multi-GPU entries, then the bench line (weak scaling + parity + config5) per transport
+N=${1:-4}
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29541 tools/dist_check.py 1024 all > gpurun_out/r02_dist_check_${N}gpu.log 2>&1; echo "dist_check exit $?"
+grep -E "DIST|exchange|unavailable|rror" gpurun_out/r02_dist_check_${N}gpu.log | tail -12
+for X in copy nccl; do
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 10 --warmup 3 --exchange $X $2 > gpurun_out/r02_bench_${N}gpu_$X.json 2> gpurun_out/r02_bench_${N}gpu_$X.err; echo "bench $X exit $?"
+  tail -2 gpurun_out/r02_bench_${N}gpu_$X.err | cut -c1-300
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/r02_bench_${N}gpu_$X.json") if l.startswith("{")][-1])
+    print("$X", round(d["value"],1), round(d["ms_per_step"],2), d["phases_ms"], d.get("parity",{}).get("ok"), d.get("config5"))
+except Exception as e: print("no json", e)
+PY
+done
