@@ -889,7 +889,7 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
 
 }  // extern "C"
 
-// Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C.  The H2D
+// Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C (S <= 12, blocks shrinking towards the end).  The H2D
 // stream brings A row blocks and B column blocks alternately (A0, B0, A1, B1, ...); as soon as block
 // pair s is on the device the compute stream scales / encodes it and multiplies everything that has
 // become computable -- the column strip (rows 0..s, column block s) and the row strip (row block s,
@@ -923,21 +923,37 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
     const bool split     = oz::host_tab::OZ_M_LO[ti] != 0.0 && h->dtype_C == GEMMUL8_F64;
 
-    // block boundaries: multiples of 256 rows / columns (whole GEMM tiles), at most 8 blocks per side
+    // Block boundaries: multiples of 256 rows / columns (whole GEMM tiles), at most 12 blocks per side, SHRINKING towards the
+    // end (weights 3 3 3 3 2 2 2 2 1 1 1 1): what is left to do when the last input byte has arrived -- the products with the
+    // last block pair and the D2H of their strips of C -- is proportional to the last block's share (1/24 instead of the 1/8
+    // of eight equal blocks), while the early blocks stay large enough for the GEMM to run at its full-size rate.
+    constexpr int kMaxBlocks = 12;
     auto bounds = [](size_t len, size_t *b) -> int {
+        static const int weight[kMaxBlocks] = {3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1};
         const size_t tiles = (len + 255) / 256;
-        const int S = (int)(tiles < 8 ? tiles : 8);
-        for (int i = 0; i <= S; ++i) { size_t x = (tiles * i / S) * 256; b[i] = x < len ? x : len; }
-        b[S] = len;
-        return S;
+        if (tiles < 24) {                       // small problems: equal blocks, at most 8
+            const int S = (int)(tiles < 8 ? (tiles ? tiles : 1) : 8);
+            for (int i = 0; i <= S; ++i) { size_t x = (tiles * i / S) * 256; b[i] = x < len ? x : len; }
+            b[S] = len;
+            return S;
+        }
+        size_t acc = 0;
+        b[0] = 0;
+        for (int i = 0; i < kMaxBlocks; ++i) {
+            acc += (size_t)weight[i];
+            size_t x = (tiles * acc / 24) * 256;
+            b[i + 1] = x < len ? x : len;
+        }
+        b[kMaxBlocks] = len;
+        return kMaxBlocks;
     };
-    size_t rb[9], cb[9];
+    size_t rb[kMaxBlocks + 1], cb[kMaxBlocks + 1];
     const int SR = bounds(m, rb), SC = bounds(n, cb);
     const int S = SR > SC ? SR : SC;
 
     struct Res {
         cudaStream_t in = nullptr, out = nullptr;
-        cudaEvent_t evA[8], evB[8], evC[16], start;
+        cudaEvent_t evA[kMaxBlocks], evB[kMaxBlocks], evC[2 * kMaxBlocks], start;
         int nev = 0;
         ~Res() {
             for (int i = 0; i < nev; ++i) { cudaEventDestroy(evA[i]); cudaEventDestroy(evB[i]); cudaEventDestroy(evC[2 * i]); cudaEventDestroy(evC[2 * i + 1]); }
@@ -949,7 +965,7 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     OZ_CUDA(cudaStreamCreateWithFlags(&r.in, cudaStreamNonBlocking), "stream");
     OZ_CUDA(cudaStreamCreateWithFlags(&r.out, cudaStreamNonBlocking), "stream");
     OZ_CUDA(cudaEventCreateWithFlags(&r.start, cudaEventDisableTiming), "event");
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kMaxBlocks; ++i) {
         OZ_CUDA(cudaEventCreateWithFlags(&r.evA[i], cudaEventDisableTiming), "event");
         OZ_CUDA(cudaEventCreateWithFlags(&r.evB[i], cudaEventDisableTiming), "event");
         OZ_CUDA(cudaEventCreateWithFlags(&r.evC[2 * i], cudaEventDisableTiming), "event");

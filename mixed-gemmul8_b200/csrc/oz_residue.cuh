@@ -61,21 +61,15 @@ __device__ __forceinline__ int residue_reference(float a, const ModConst &c) {
 //     +128, the same int8 as the reference's -128).  t is evaluated modulo 2^32 on the low words (|t| < 2^10).
 //     Valid for |a| < 2^57 (fp64) / 2^24 (fp32);
 //   * m = 256 (modulus 0) needs no arithmetic at all: the int8 is the low byte of a;
-//   * larger values (more than 15 moduli) are split exactly as a = h * 2^32 + l, |h| < 2^57,
-//     |l| < 2^32, and joined as (res(h) * (2^32 mod m) + res(l)) mod m.
+//   * larger values (more than 15 moduli; |a| < 2^89) are split exactly as a = h * 2^44 + l, |h| < 2^45, |l| < 2^44, and
+//     folded BEFORE the reduction: v = h * c + l with c = 2^44 mod m (symmetric, |c| <= 128) is congruent to a, an exact
+//     integer below 2^53 (one DFMA), and takes the short route; its low word is h_lo * c + l_lo in 32-bit arithmetic.
+//     Two FP64 instructions and two IMADs per (element, modulus) -- the first version reduced h and l separately and
+//     joined the residues (three reductions, ~18 instructions), which made the encoder compute-bound from 17 moduli on
+//     (scaling phase 15 ms instead of 3.6 at 16384^2 x 16384).
 template <typename R> struct SmallLimit;
 template <> struct SmallLimit<double> { static constexpr double value = 0x1p57; };
 template <> struct SmallLimit<float> { static constexpr float value = 0x1p24f; };
-__device__ __forceinline__ int fold_once(int ti, int half, int m) {   // [-m/2 - m, m/2 + m] -> symmetric
-    asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.gt.s32 p, %0, %1;\n\t"
-        "@p sub.s32 %0, %0, %2;\n\t"
-        "setp.lt.s32 q, %0, %3;\n\t"
-        "@q add.s32 %0, %0, %2;\n\t}"
-        : "+r"(ti)
-        : "r"(half), "r"(m), "r"(-half));
-    return ti;
-}
 __device__ __forceinline__ int fold_down(int ti, int half, int m) {   // (-m/2, m + m/2) -> symmetric
     asm("{\n\t.reg .pred p;\n\t"
         "setp.gt.s32 p, %0, %1;\n\t"
@@ -95,15 +89,10 @@ __device__ __forceinline__ int residue_small(float a, int a_lo, const ModConst &
     const int q = __float_as_int(__fmaf_rd(a, c.rcpf, 12582912.0f)) - 0x4B400000;  // 1.5 * 2^23
     return fold_down(q * c.neg_mi + a_lo, c.half, c.m);
 }
-// exact residue of an int t, |t| < 2^22, by the same trick in fp32
-__device__ __forceinline__ int residue_int(int t, const ModConst &c) {
-    const float f = __int_as_float(0x4B400000 + t) - 12582912.0f;
-    const int q   = __float_as_int(__fmaf_rn(f, c.rcpf, 12582912.0f)) - 0x4B400000;
-    return fold_once(q * c.neg_mi + t, c.half, c.m);
-}
-// |a| < 2^89 through the halves h = trunc(a / 2^32), l = a - h * 2^32
-__device__ __forceinline__ int residue_big(double h, int h_lo, double l, int l_lo, int pow32, const ModConst &c) {
-    return residue_int(residue_small(h, h_lo, c) * pow32 + residue_small(l, l_lo, c), c);
+// |a| < 2^89 through the halves h = trunc(a / 2^44), l = a - h * 2^44: v = h * (2^44 mod m) + l is exact and congruent to a
+__device__ __forceinline__ int residue_big(double h, int h_lo, double l, int l_lo, double pow44, int pow44_i, const ModConst &c) {
+    const double v = fma(h, pow44, l);                   // |v| <= 2^45 * 128 + 2^44 < 2^53: exact
+    return residue_small(v, h_lo * pow44_i + l_lo, c);   // low word of v modulo 2^32
 }
 
 // Residues of G integer-valued elements for every modulus; `store(j, r)` receives the G residues of
@@ -115,7 +104,9 @@ __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned n
     unsigned top = 0;   // |v| < 2^57 on the high words (integer compare: keeps the test off the FP64 pipe)
 #pragma unroll
     for (int e = 0; e < G; ++e) top = max(top, (unsigned)__double2hiint(v[e]) & 0x7fffffffu);
-    const bool small = top < 0x43800000u;
+    // (SPLIT kernels: one decision per warp -- the long route is valid for small values too, and a warp whose lanes disagree
+    //  would execute both; with 17 moduli about half of the threads of a warp hold a value beyond 2^57)
+    const bool small = SPLIT ? __all_sync(__activemask(), top < 0x43800000u) != 0 : top < 0x43800000u;
     if (reference_chain || (!SPLIT && !small)) {
         for (unsigned j = 0; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
@@ -144,19 +135,20 @@ __device__ __forceinline__ void residues_double(const double (&v)[G], unsigned n
         int hlo[G], llo[G];
 #pragma unroll
         for (int e = 0; e < G; ++e) {
-            h[e]   = trunc(v[e] * 0x1p-32);
-            l[e]   = fma(h[e], -4294967296.0, v[e]);
+            h[e]   = trunc(v[e] * 0x1p-44);
+            l[e]   = fma(h[e], -17592186044416.0, v[e]);
             hlo[e] = low_word(h[e]);
             llo[e] = low_word(l[e]);
             asm volatile("" : "+r"(hlo[e]), "+r"(llo[e]));
         }
-        store(0u, llo);  // 2^32 = 0 mod 256
+        store(0u, llo);  // 2^44 = 0 mod 256
         for (unsigned j = 1; j < num_moduli; ++j) {
             const ModConst c = load_mod(j);
-            const int p32    = dev_tab::OZ_POW32[j];
+            const double p44 = dev_tab::OZ_POW44[j];
+            const int p44i   = (int)p44;
             int r[G];
 #pragma unroll
-            for (int e = 0; e < G; ++e) r[e] = residue_big(h[e], hlo[e], l[e], llo[e], p32, c);
+            for (int e = 0; e < G; ++e) r[e] = residue_big(h[e], hlo[e], l[e], llo[e], p44, p44i, c);
             store(j, r);
         }
     }

@@ -3,7 +3,7 @@
  * (oz_tables.inc), same operation order; fma_rd is fma() under FE_DOWNWARD.
  *   residue_model_small_d / _f : floor quotient from the low word of fma_rd(a, rcp, 1.5 * 2^52 | 2^23), t = a - q m on the
  *                                low 32 bits, one fold "t > m/2 ? t - m : t"
- *   residue_model_big_d        : a = h 2^32 + l, (res(h) * (2^32 mod m) + res(l)) mod m
+ *   residue_model_big_d        : a = h 2^44 + l, v = h * (2^44 mod m) + l (exact, < 2^53), then the short route on v
  * Each returns the int8 the encoder would store.  */
 #include <fenv.h>
 #include <math.h>
@@ -20,11 +20,6 @@ static int32_t low_word_d(double a) { return (int32_t)(uint32_t)(uint64_t)(int64
 static int32_t low_word_f(float a) { return (int32_t)a; }
 
 static int32_t fold_down(int32_t t, int32_t half, int32_t m) { return t > half ? t - m : t; }
-static int32_t fold_once(int32_t t, int32_t half, int32_t m) {
-    if (t > half) t -= m;
-    if (t < -half) t += m;
-    return t;
-}
 
 static double fma_rd(double a, double b, double c) {
     volatile double x = a, y = b, z = c, r;
@@ -63,19 +58,13 @@ int residue_model_small_f(float a, unsigned j) {
     return (int8_t)fold_down(t, m >> 1, m);
 }
 
-static int32_t residue_int(int32_t t, unsigned j) {                    /* |t| < 2^22, nearest quotient + two-sided fold */
-    const int32_t m = OZ_MOD[j];
-    uint32_t fb = 0x4B400000u + (uint32_t)t; float f; memcpy(&f, &fb, 4);
-    f -= 12582912.0f;
-    const float r = fmaf(f, OZ_RCP32[j], 12582912.0f);
-    uint32_t bits; memcpy(&bits, &r, 4);
-    const int32_t q = (int32_t)bits - 0x4B400000;
-    return fold_once(q * (-m) + t, m >> 1, m);
-}
 int residue_model_big_d(double a, unsigned j) {
-    const double h = trunc(a * 0x1p-32), l = fma(h, -4294967296.0, a);
+    const double h = trunc(a * 0x1p-44), l = fma(h, -17592186044416.0, a);
     const int32_t hlo = low_word_d(h), llo = low_word_d(l);
     if (j == 0) return (int8_t)llo;
-    return (int8_t)residue_int(small_d(h, hlo, j) * OZ_POW32[j] + small_d(l, llo, j), j);
+    const double c = OZ_POW44[j];
+    const double v = fma(h, c, l);                                       /* exact: |v| < 2^53 */
+    const int32_t vlo = (int32_t)((uint32_t)hlo * (uint32_t)(int32_t)c + (uint32_t)llo);
+    return (int8_t)small_d(v, vlo, j);
 }
 int residue_model_modulus(unsigned j) { return OZ_MOD[j]; }

@@ -256,6 +256,8 @@ def emit(t, path):
     s += arr("OZ_RCP32", "float", t["rcp32"], hxf)
     # 2^32 mod m_j, symmetric representative: joins the two halves of values beyond 2^57 in the encoder
     s += arr("OZ_POW32", "int", [((1 << 32) % m) - (m if ((1 << 32) % m) > m // 2 else 0) for m in t["mod"]], str)
+    # 2^44 mod m_j, symmetric, as a double: values beyond 2^57 are split as h * 2^44 + l and folded as h * c + l (exact, < 2^53)
+    s += arr("OZ_POW44", "double", [float(((1 << 44) % m) - (m if ((1 << 44) % m) > m // 2 else 0)) for m in t["mod"]], hx)
     # epilogue Barrett constants (oz_tcgen05.cuh: reduce_mod_u): floor(2^32 / m_j), 2^32 - m_j, and the multiple of m_j that
     # shifts any product |x| <= 2^17 * 127^2 into the unsigned range
     s += arr("OZ_BARRETT_INV", "unsigned", [(1 << 32) // m for m in t["mod"]], lambda v: f"{v}u")
