@@ -66,12 +66,15 @@ typedef struct {
     unsigned num_moduli;
     int fastmode;
     void *work;                  /* device, >= gemmul8_b200_pgemm_worksize bytes */
-    int dtype_A, dtype_B, dtype_C; /* gemmul8_dtype_t, real types */
+    int dtype_A, dtype_B, dtype_C; /* gemmul8_dtype_t; complex types: fast mode only (panels are assembled, then one call) */
+    int compute_type;            /* gemmul8_compute_t: REAL_DEFAULT for real types, COMPLEX_* for complex types */
     void *stream;                /* cudaStream_t of the compute work */
     unsigned flags;              /* GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_PHASE_LOG as for gemmul8_b200_gemm_part */
     double timers_ns[4];
 } gemmul8_b200_pargs;
 
+/* bytes of `work` for the rank's (m/P) x (n/Q) block: the single-GPU workSize of that block (real types; for complex types ask
+ * the single-GPU library for the block's workSize with the compute type) */
 size_t gemmul8_b200_pgemm_worksize(const gemmul8_b200_grid *grid, size_t m, size_t n, size_t k, unsigned num_moduli);
 int gemmul8_b200_pgemm(gemmul8_b200_grid *grid, gemmul8_b200_pargs *args);
 

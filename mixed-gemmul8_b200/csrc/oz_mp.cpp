@@ -52,7 +52,8 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 constexpr int kMaxPieces = 4;    // row pieces of the A panel
 constexpr int kMaxSide   = 16;   // P, Q <= 16
 
-size_t elem_size(int dt) { return dt == GEMMUL8_F32 ? 4 : 8; }
+size_t elem_size(int dt) { return dt == GEMMUL8_F32 ? 4 : dt == GEMMUL8_C64 ? 16 : 8; }
+bool is_complex(int dt) { return dt == GEMMUL8_C32 || dt == GEMMUL8_C64; }
 
 // driver entry points (stream memory operations), resolved once
 struct Driver {
@@ -305,8 +306,11 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     for (double &t : a->timers_ns) t = 0.0;
     const size_t P = (size_t)g->P, Q = (size_t)g->Q;
     if (a->m % P || a->n % (P * Q) || a->k % Q) return fail(GEMMUL8_ERR_ARGUMENT, "pgemm: m % P, n % (P Q) and k % Q must be 0");
-    if (a->dtype_A > GEMMUL8_F64 || a->dtype_B > GEMMUL8_F64 || a->dtype_C > GEMMUL8_F64 || a->dtype_A < 0 || a->dtype_B < 0 || a->dtype_C < 0)
-        return fail(GEMMUL8_ERR_ARGUMENT, "pgemm: real types only");
+    if (a->dtype_A > GEMMUL8_C64 || a->dtype_B > GEMMUL8_C64 || a->dtype_C > GEMMUL8_C64 || a->dtype_A < 0 || a->dtype_B < 0 || a->dtype_C < 0)
+        return fail(GEMMUL8_ERR_ARGUMENT, "pgemm: bad dtype tag");
+    const bool cplx = is_complex(a->dtype_C);
+    if (cplx && !a->fastmode && g->nranks > 1)
+        return fail(GEMMUL8_ERR_ARGUMENT, "pgemm: complex types are partitioned in fast mode only (the accurate-mode bound exchange is real-only)");
     const size_t m_loc = a->m / P, n_loc = a->n / Q, k = a->k, kq = k / Q, w = n_loc / P;
     const size_t esA = elem_size(a->dtype_A), esB = elem_size(a->dtype_B);
     if (m_loc == 0 || n_loc == 0) return GEMMUL8_OK;
@@ -315,7 +319,7 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     if ((Q > 1 && a->lda < m_loc) || (P > 1 && a->ldb < k)) return fail(GEMMUL8_ERR_ARGUMENT, "pgemm: leading dimension too small");
     cudaStream_t st = static_cast<cudaStream_t>(a->stream);
     const bool copy = g->exchange == GEMMUL8_MP_EXCHANGE_COPY && g->nranks > 1;
-    const bool pipelined = a->fastmode != 0 && k > 0;
+    const bool pipelined = a->fastmode != 0 && k > 0 && !cplx;   // the block-wise entry is real-only; complex: whole panels, one call
     const uint32_t epoch = ++g->epoch;
 
     // full-problem argument block of this rank's C block (panels: grid buffers, or the caller's slices where nothing is exchanged)
@@ -326,7 +330,7 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     ga.A = Q > 1 ? (const void *)g->a_buf : a->a_slice; ga.lda = Q > 1 ? m_loc : a->lda;
     ga.B = P > 1 ? (const void *)g->b_buf : a->b_slice; ga.ldb = P > 1 ? k : a->ldb;
     ga.C = a->c_block; ga.ldc = a->ldc;
-    ga.num_moduli = a->num_moduli; ga.fastmode = a->fastmode; ga.work = a->work; ga.compute_type = GEMMUL8_REAL_DEFAULT;
+    ga.num_moduli = a->num_moduli; ga.fastmode = a->fastmode; ga.work = a->work; ga.compute_type = cplx ? a->compute_type : GEMMUL8_REAL_DEFAULT;
     ga.dtype_A = a->dtype_A; ga.dtype_B = a->dtype_B; ga.dtype_C = a->dtype_C;
     ga.stream = a->stream; ga.flags = a->flags | (copy ? (unsigned)GEMMUL8_FLAG_EXCLUSIVE_SMS : 0u);
 

@@ -19,7 +19,7 @@ class PArgs(C.Structure):
     _fields_ = [("m", C.c_size_t), ("n", C.c_size_t), ("k", C.c_size_t), ("alpha", C.c_void_p),
                 ("a_slice", C.c_void_p), ("lda", C.c_size_t), ("b_slice", C.c_void_p), ("ldb", C.c_size_t), ("beta", C.c_void_p),
                 ("c_block", C.c_void_p), ("ldc", C.c_size_t), ("num_moduli", C.c_uint), ("fastmode", C.c_int), ("work", C.c_void_p),
-                ("dtype_A", C.c_int), ("dtype_B", C.c_int), ("dtype_C", C.c_int), ("stream", C.c_void_p), ("flags", C.c_uint),
+                ("dtype_A", C.c_int), ("dtype_B", C.c_int), ("dtype_C", C.c_int), ("compute_type", C.c_int), ("stream", C.c_void_p), ("flags", C.c_uint),
                 ("timers_ns", C.c_double * 4)]
 
 
@@ -91,7 +91,8 @@ class Grid:
     def worksize(self, m, n, k, num_moduli):
         return lib().gemmul8_b200_pgemm_worksize(self.handle, m, n, k, num_moduli)
 
-    def pgemm(self, m, n, k, alpha, a_slice, lda, b_slice, ldb, beta, c_block, ldc, num_moduli, fastmode, work, flags=0, stream=None):
+    def pgemm(self, m, n, k, alpha, a_slice, lda, b_slice, ldb, beta, c_block, ldc, num_moduli, fastmode, work, flags=0, stream=None,
+              computeType=0):
         """C_block(p, q) = alpha * A_panel(p) * B_panel(q) + beta * C_block; tensors hold column-major data (see the header)."""
         import torch
         from . import _dtype_tag, _scalar_buf
@@ -102,6 +103,7 @@ class Grid:
         a.alpha, a.beta = C.addressof(al), C.addressof(be)
         a.a_slice, a.lda, a.b_slice, a.ldb, a.c_block, a.ldc = a_slice.data_ptr(), lda, b_slice.data_ptr(), ldb, c_block.data_ptr(), ldc
         a.num_moduli, a.fastmode, a.work, a.flags = num_moduli, int(bool(fastmode)), work.data_ptr(), flags
+        a.compute_type = computeType
         a.stream = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         _check(lib().gemmul8_b200_pgemm(self.handle, C.byref(a)))
         return list(a.timers_ns)

@@ -84,6 +84,32 @@ def cpp_pgemm(mpgrid):
     return f
 
 
+def complex_check(grid, mg):
+    """ZGEMM through the C ABI pgemm (fast mode, Karatsuba): this rank's block against one gemm call on the gathered panels."""
+    KARA = 3
+    m, n, k, N = grid.P * 512, grid.Q * grid.P * 256, grid.Q * 384, 14
+    m_loc, n_loc = grid.block_dims(m, n)
+    klo, khi = grid.a_slice_k(k)
+    clo, chi = grid.b_slice_cols(n_loc)
+    rank = dist.get_rank()
+    a_slice = g.phi_matrix(m_loc, khi - klo, 0.5, torch.complex128, seed=300 + 17 * rank)
+    b_slice = g.phi_matrix(k, chi - clo, 0.5, torch.complex128, seed=400 + 17 * rank)
+    work = torch.empty(g.workSize(m_loc, n_loc, k, N, KARA), dtype=torch.uint8, device="cuda")
+    C1 = torch.zeros((n_loc, m_loc), dtype=torch.complex128, device="cuda")
+    mg.pgemm(m, n, k, 1.0, a_slice, m_loc, b_slice, k, 0.0, C1, m_loc, N, True, work, computeType=KARA)
+    a_panel = grid.gather_a_panel(a_slice, m_loc, k)
+    b_panel = grid.gather_b_panel(b_slice, n_loc, k)
+    C2 = torch.zeros_like(C1)
+    g.gemm(None, 0, 0, m_loc, n_loc, k, 1.0, a_panel, m_loc, b_panel, k, 0.0, C2, m_loc, N, True, work, computeType=KARA)
+    torch.cuda.synchronize()
+    same = torch.equal(torch.view_as_real(C1), torch.view_as_real(C2)) and bool(C1.abs().sum() > 0)
+    flag = torch.tensor([0 if same else 1], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print(f"complex128 Karatsuba through pgemm: identical={flag.item() == 0}", flush=True)
+    return flag.item() == 0
+
+
 def make_mp_grid(grid, a_bytes, b_bytes, want="copy"):
     """The C++ grid with the copy-engine exchange, or (if CUDA IPC / peer access is unavailable, or asked for) NCCL."""
     mp = import_module("gemmul8_b200.mp")
@@ -115,12 +141,12 @@ def main():
         if name == "python":
             res = run_checks(grid, dmod, S)
         else:
-            cap = 8 * max(S * S, 1280 * 4 * 640, 4 * 640 * 768)
+            cap = 16 * max(S * S, 1280 * 4 * 640, 4 * 640 * 768)
             mg, how = make_mp_grid(grid, cap, cap, name)
             res = run_checks(grid, dmod, S, pgemm=cpp_pgemm(mg))
             # the same grid again: epochs, acknowledgements and buffer reuse across calls
             res2 = run_checks(grid, dmod, S // 2, verbose=False, pgemm=cpp_pgemm(mg))
-            res["ok"] = res["ok"] and res2["ok"]
+            res["ok"] = res["ok"] and res2["ok"] and complex_check(grid, mg)
             mg.close()
             if dist.get_rank() == 0:
                 print(f"C ABI pgemm, exchange: {how}", flush=True)
