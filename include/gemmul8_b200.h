@@ -123,7 +123,8 @@ int gemmul8_b200_init(int device);
 /* Tuning / debug options, process-wide and thread-safe.  Their defaults come from the environment, read once:
  *   "gemm_pair"  (OZ_GEMM_PAIR)  -1 auto | 0 single-CTA kernel | 1 CTA-pair kernel      "band" (OZ_BAND), "pair_band" (OZ_PAIR_BAND)
  *   "pair_stages" (OZ_PAIR_STAGES) 0 auto | 4 | 5 | 6     "encode_reference" (GEMMUL8_B200_ENCODE=reference) 0 | 1
- *   "fused_k" (GEMMUL8_B200_FUSED_K) largest k that takes the single-kernel product + CRT path (0 = never) */
+ *   "fused_k" (GEMMUL8_B200_FUSED_K) largest k that takes the single-kernel product + CRT path (0 = never)
+ *   "scale_fork" (GEMMUL8_B200_SCALE_FORK) 1 | 0: small operands are scaled on two streams side by side */
 int gemmul8_b200_set_option(const char *name, int value);
 int gemmul8_b200_get_option(const char *name, int *value);
 
@@ -152,7 +153,7 @@ int gemmul8_b200_gemm_host(gemmul8_b200_args *args_with_host_matrices, void *dev
 enum { GEMMUL8_PART_SCALE_A = 1, GEMMUL8_PART_SCALE_B = 2, GEMMUL8_PART_PRODUCT = 4 };
 int gemmul8_b200_gemm_part(gemmul8_b200_args *args, int parts, size_t row0, size_t row1, size_t col0, size_t col1);
 
-/* Low-memory call (real types, fast and accurate mode).  gemm() keeps the residue slices of ALL of op(A) and
+/* Low-memory call (real types: fast and accurate mode; complex types: fast mode).  gemm() keeps the residue slices of ALL of op(A) and
  * op(B) resident -- N (m + n) k bytes, 184 GiB at 65536^3 (GEMMul8/src/gemmul8.cu:27-60); the reference's
  * README.md:3 points at a `memory-lt` branch for this, which is not in the tree.  Here C is produced in blocks of
  * block_rows x block_cols (multiples of 256, or the whole dimension) and `args->work` only needs
@@ -162,6 +163,10 @@ int gemmul8_b200_gemm_part(gemmul8_b200_args *args, int parts, size_t row0, size
  * the least re-encoding for a workspace of at most `max_bytes`.  timers_ns (GEMMUL8_FLAG_TIMERS) are the sums of the
  * phases over all blocks, as in gemmul8_b200_gemm. */
 size_t gemmul8_b200_worksize_blocked(size_t m, size_t n, size_t k, unsigned num_moduli, size_t block_rows, size_t block_cols);
+/* Complex types (fast mode only): gemm_blocked runs one complete complex call per C block in a workspace of
+ * workSize(block_rows, block_cols, k, N, compute_type) bytes -- this function returns exactly that (0 for bad blocks). */
+size_t gemmul8_b200_worksize_blocked_complex(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type, size_t block_rows,
+                                             size_t block_cols);
 int gemmul8_b200_plan_blocks(size_t m, size_t n, size_t k, unsigned num_moduli, size_t max_bytes,
                              size_t *block_rows, size_t *block_cols, size_t *work_bytes);
 int gemmul8_b200_gemm_blocked(gemmul8_b200_args *args, size_t block_rows, size_t block_cols);

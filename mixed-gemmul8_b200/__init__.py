@@ -30,7 +30,7 @@ FLAG_DEVICE_SCALARS, FLAG_EXCLUSIVE_SMS = 1 << 16, 1 << 17
 EXPORTED_SYMBOLS = (
     "gemmul8_b200_worksize", "gemmul8_b200_work_layout", "gemmul8_b200_gemm", "gemmul8_b200_host_scratch_size",
     "gemmul8_b200_gemm_host", "gemmul8_b200_gemm_part",
-    "gemmul8_b200_worksize_blocked", "gemmul8_b200_plan_blocks", "gemmul8_b200_gemm_blocked", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
+    "gemmul8_b200_worksize_blocked", "gemmul8_b200_worksize_blocked_complex", "gemmul8_b200_plan_blocks", "gemmul8_b200_gemm_blocked", "gemmul8_b200_product_i32", "gemmul8_b200_modulus", "gemmul8_b200_crt_weight",
     "gemmul8_b200_phase_log_collect", "gemmul8_b200_launch_count", "gemmul8_b200_last_error", "gemmul8_b200_version",
     "gemmul8_b200_init", "gemmul8_b200_set_option", "gemmul8_b200_get_option",
 )
@@ -91,6 +91,8 @@ def lib():
         L.gemmul8_b200_gemm_part.argtypes = [C.POINTER(Args), C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
         L.gemmul8_b200_worksize_blocked.restype = C.c_size_t
         L.gemmul8_b200_worksize_blocked.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, C.c_size_t, C.c_size_t]
+        L.gemmul8_b200_worksize_blocked_complex.restype = C.c_size_t
+        L.gemmul8_b200_worksize_blocked_complex.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, C.c_int, C.c_size_t, C.c_size_t]
         L.gemmul8_b200_plan_blocks.restype = C.c_int
         L.gemmul8_b200_plan_blocks.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, C.c_size_t] + [C.POINTER(C.c_size_t)] * 3
         L.gemmul8_b200_gemm_blocked.restype = C.c_int
@@ -243,14 +245,19 @@ def plan_blocks(m, n, k, num_moduli, max_bytes):
     return mb.value, nb.value, wb.value
 
 
+def workSizeBlockedComplex(m, n, k, num_moduli, computeType, block_rows, block_cols):
+    """Bytes of `work` for gemm_blocked on complex types (fast mode): workSize of one block."""
+    return lib().gemmul8_b200_worksize_blocked_complex(m, n, k, num_moduli, computeType, block_rows, block_cols)
+
+
 def gemm_blocked(handle, op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, work,
-                 block_rows, block_cols, flags=0):
+                 block_rows, block_cols, flags=0, computeType=REAL_DEFAULT):
     """gemm() with a small workspace: C in blocks of block_rows x block_cols, `work` of workSizeBlocked() bytes
     (gemmul8_b200_gemm_blocked; real types).  Same result bits as gemm()."""
     stream = None
     if handle is not None:
         stream = handle.cuda_stream if hasattr(handle, "cuda_stream") else int(handle)
-    a = make_args(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, work, REAL_DEFAULT, stream, flags)
+    a = make_args(op_A, op_B, m, n, k, alpha, A, lda, B, ldb, beta, Cmat, ldc, num_moduli, fastmode, work, computeType, stream, flags)
     _check(lib().gemmul8_b200_gemm_blocked(C.byref(a), block_rows, block_cols))
     return list(a.timers_ns)
 

@@ -35,6 +35,7 @@ Option g_options[] = {
     {"pair_stages", "OZ_PAIR_STAGES", {0}, 0, 7},
     {"encode_reference", nullptr, {0}, 0, 1},
     {"fused_k", "GEMMUL8_B200_FUSED_K", {0}, 0, 1 << 17},
+    {"scale_fork", "GEMMUL8_B200_SCALE_FORK", {1}, 0, 1},
 };
 std::once_flag g_options_once;
 void load_options_from_env() {
@@ -65,6 +66,7 @@ const Tuning &tuning() {
     t.pair_stages      = g_options[3].value.load(std::memory_order_relaxed);
     t.encode_reference = g_options[4].value.load(std::memory_order_relaxed);
     t.fused_k          = g_options[5].value.load(std::memory_order_relaxed);
+    t.scale_fork       = g_options[6].value.load(std::memory_order_relaxed);
     return t;
 }
 }  // namespace oz
@@ -386,12 +388,29 @@ int gemm_real(gemmul8_b200_args *a) {
         // (a distributed caller overlaps the arrival of the B panel with the scaling of A: two calls,
         //  GEMMUL8_FLAG_ONLY_SCALE_A then GEMMUL8_FLAG_SKIP_SCALE_A; see mixed-gemmul8_b200/distributed.py)
         int rc = GEMMUL8_OK;
-        if (!(a->flags & GEMMUL8_FLAG_SKIP_SCALE_A))
+        // Small operands: the four scaling launches (shift A, encode A, shift B, encode B) are latency-bound -- at 1024^3 they
+        // are 39 of the call's 64 us -- and A's chain does not depend on B's.  B's chain goes to a side stream (forked and
+        // joined with events, so the call stays stream-ordered and capturable) and the two run side by side.
+        const bool fork = oz::tuning().scale_fork != 0 && !(a->flags & (GEMMUL8_FLAG_SKIP_SCALE_A | GEMMUL8_FLAG_ONLY_SCALE_A)) &&
+                          (m * k + k * n) * 8 <= ((size_t)96 << 20) && g_side.init();
+        if (fork) {
+            SideStreams &S = g_side;
+            OZ_CUDA(cudaEventRecord(S.start, st), "event record");
+            OZ_CUDA(cudaStreamWaitEvent(S.sB, S.start, 0), "stream wait");
+            rc = scale_operand(a->dtype_B, b_strided, a->B, a->ldb, n, k, ref_width, l2, N, B8i, L.lda8i, L.sizeB, sftB, true, S.sB);
+            if (rc) return rc;
+            OZ_CUDA(cudaEventRecord(S.done, S.sB), "event record");
             rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, l2, N, A8i, L.lda8i, L.sizeA, sftA, true, st);
-        if (rc) return rc;
-        if (a->flags & GEMMUL8_FLAG_ONLY_SCALE_A) { timer.mark(); timer.finish(a->timers_ns); return GEMMUL8_OK; }
-        rc = scale_operand(a->dtype_B, b_strided, a->B, a->ldb, n, k, ref_width, l2, N, B8i, L.lda8i, L.sizeB, sftB, true, st);
-        if (rc) return rc;
+            if (rc) return rc;
+            OZ_CUDA(cudaStreamWaitEvent(st, S.done, 0), "stream wait");
+        } else {
+            if (!(a->flags & GEMMUL8_FLAG_SKIP_SCALE_A))
+                rc = scale_operand(a->dtype_A, a_strided, a->A, a->lda, m, k, ref_width, l2, N, A8i, L.lda8i, L.sizeA, sftA, true, st);
+            if (rc) return rc;
+            if (a->flags & GEMMUL8_FLAG_ONLY_SCALE_A) { timer.mark(); timer.finish(a->timers_ns); return GEMMUL8_OK; }
+            rc = scale_operand(a->dtype_B, b_strided, a->B, a->ldb, n, k, ref_width, l2, N, B8i, L.lda8i, L.sizeB, sftB, true, st);
+            if (rc) return rc;
+        }
     } else {
         if (a->flags & GEMMUL8_FLAG_ONLY_SCALE_A) return GEMMUL8_OK;   // accurate mode needs both operands: all work in the second call
         // reference: int8tc::scaling, GEMMul8/src/scaling.hpp:3053-3136
@@ -850,6 +869,13 @@ int gemm_blocked_real(gemmul8_b200_args *a, const BlockPlan &P) {
 
 extern "C" {
 
+size_t gemmul8_b200_worksize_blocked_complex(size_t m, size_t n, size_t k, unsigned num_moduli, int compute_type, size_t block_rows,
+                                             size_t block_cols) {
+    const size_t mb = block_rows < m ? block_rows : m, nb = block_cols < n ? block_cols : n;
+    if (mb == 0 || nb == 0 || (mb < m && mb % 256) || (nb < n && nb % 256) || compute_type < 1 || compute_type > 3) return 0;
+    return gemmul8_b200_worksize(mb, nb, k, num_moduli, compute_type);
+}
+
 size_t gemmul8_b200_worksize_blocked(size_t m, size_t n, size_t k, unsigned num_moduli, size_t block_rows, size_t block_cols) {
     BlockPlan P;
     if (num_moduli < 2 || num_moduli > 20 || !carve_blocks(m, n, k, num_moduli, block_rows, block_cols, P)) return 0;
@@ -872,8 +898,39 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
     if (a) for (double &t : a->timers_ns) t = 0.0;
     int rc = check_args(a);
     if (rc) return rc;
-    if (is_complex(a->dtype_C)) return fail(GEMMUL8_ERR_ARGUMENT, "gemm_blocked: real types only (complex sizes that need it exceed k <= 2^16 first)");
     if (a->m == 0 || a->n == 0) return GEMMUL8_OK;
+    if (is_complex(a->dtype_C)) {
+        // Complex types, fast mode: every C block is one complete complex call on its row block of op(A) and column block of
+        // op(B), in a workspace of workSize(block_rows, block_cols, k, N, compute_type) bytes.  Fast-mode shifts depend on the
+        // row / column alone, so the bits are those of gemm(); an operand block is re-encoded for every block it meets
+        // (encoding is ~10 % of a complex call).  Accurate mode needs the bound product of the whole matrix: not blocked.
+        if (!a->fastmode) return fail(GEMMUL8_ERR_ARGUMENT, "gemm_blocked: complex types in fast mode only");
+        if (a->k > (size_t(1) << 16)) return fail(GEMMUL8_ERR_ARGUMENT, "complex types: k must be <= 2^16 (int32 accumulation)");
+        const size_t mb = block_rows < a->m ? block_rows : a->m, nb = block_cols < a->n ? block_cols : a->n;
+        if (mb == 0 || nb == 0 || (mb < a->m && mb % 256) || (nb < a->n && nb % 256))
+            return fail(GEMMUL8_ERR_ARGUMENT, "gemm_blocked: block sizes must be multiples of 256 (or cover the whole dimension)");
+        if (a->k == 0) {
+            OZ_CUDA(oz::launch_scale_c(a->dtype_C, a->m, a->n, a->C, a->ldc, a->beta, dev_scalars(a), static_cast<cudaStream_t>(a->stream)), "scale C");
+            return GEMMUL8_OK;
+        }
+        const size_t esA = elem_size(a->dtype_A), esB = elem_size(a->dtype_B), esC = elem_size(a->dtype_C);
+        const bool a_rows = a->op_A == GEMMUL8_OP_N, b_rows = a->op_B != GEMMUL8_OP_N;   // the block index runs along stored rows
+        for (size_t r0 = 0; r0 < a->m; r0 += mb) {
+            for (size_t c0 = 0; c0 < a->n; c0 += nb) {
+                gemmul8_b200_args s = *a;
+                s.m = r0 + mb < a->m ? mb : a->m - r0;
+                s.n = c0 + nb < a->n ? nb : a->n - c0;
+                s.A = static_cast<const uint8_t *>(a->A) + (a_rows ? r0 : r0 * a->lda) * esA;
+                s.B = static_cast<const uint8_t *>(a->B) + (b_rows ? c0 : c0 * a->ldb) * esB;
+                s.C = static_cast<uint8_t *>(a->C) + (c0 * a->ldc + r0) * esC;
+                s.flags = a->flags & ~(unsigned)GEMMUL8_FLAG_PHASE_LOG;
+                rc = gemm_complex(&s);
+                if (rc) return rc;
+                for (int t = 0; t < 4; ++t) a->timers_ns[t] += s.timers_ns[t];
+            }
+        }
+        return GEMMUL8_OK;
+    }
     BlockPlan P;
     if (!carve_blocks(a->m, a->n, a->k, a->num_moduli, block_rows, block_cols, P))
         return fail(GEMMUL8_ERR_ARGUMENT, "gemm_blocked: block sizes must be multiples of 256 (or cover the whole dimension)");

@@ -218,3 +218,27 @@ def test_no_writes_outside_workspace_and_c(g, monkeypatch):
             check(cbuf, coff, m * n * es, ("C", m, n, k, N, ct, pair))
             assert torch.isfinite(torch.view_as_real(C) if C.is_complex() else C).all()
     g.set_option("gemm_pair", -1)
+
+
+@pytest.mark.parametrize("ct", [BIG, CLASSIC, KARA])
+@pytest.mark.parametrize("opA,opB", [(0, 0), (2, 1)])
+def test_complex_low_memory_call_equals_gemm(g, ct, opA, opB):
+    """gemmul8_b200_gemm_blocked on complex types (fast mode): C block by block in a workspace of workSize(block) bytes, same
+    bits as gemm() (fast-mode shifts depend on the row / column alone), nothing written beyond the block workspace."""
+    torch = torch_()
+    m, n, k, N = 700, 600, 320, 14
+    A, B = operands(g, m, n, k, opA, opB, torch.complex128, torch.complex128)
+    C0 = g.phi_matrix(m, n, 1.0, torch.complex128, seed=5)
+    ws = g.workSize(m, n, k, N, ct)
+    Cf, _ = run(ours(g), ws, g, m, n, k, N, True, A, B, opA, opB, torch.complex128, ct, alpha=0.5 + 1j, beta=-2.0, C0=C0)
+    mb, nb = 256, 512
+    wsb = g.workSizeBlockedComplex(m, n, k, N, ct, mb, nb)
+    assert 0 < wsb < ws and wsb == g.workSize(mb, nb, k, N, ct)
+    buf = torch.full((wsb + 4096,), 0xA5, dtype=torch.uint8, device="cuda")
+    Cb = C0.clone()
+    g.gemm_blocked(None, opA, opB, m, n, k, 0.5 + 1j, A, A.shape[1], B, B.shape[1], -2.0, Cb, m, N, True, buf[:wsb], mb, nb, computeType=ct)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(Cb), torch.view_as_real(Cf))
+    assert bool((buf[wsb:] == 0xA5).all())
+    with pytest.raises(g.Gemmul8Error):          # accurate mode is not blocked for complex types
+        g.gemm_blocked(None, opA, opB, m, n, k, 1.0, A, A.shape[1], B, B.shape[1], 0.0, Cb, m, N, False, buf[:wsb], mb, nb, computeType=ct)
