@@ -83,3 +83,24 @@ def test_round2_drivers_accuracy_tables_identical_between_libraries():
                 assert row == ref[key], (prec, key)
                 n += len(row)
         assert n == cells
+
+
+def test_round2_drivers_timing_rows_carry_identical_errors_and_are_faster():
+    """flops_check of test_mixed_double and test_float_complex (sizes 1024 .. 8192, 2 .. 20 moduli, fast and accurate): every
+    emulation row has the same relerr_max / relerr_med strings with both libraries, and this library is the faster one."""
+    t = _tool()
+    for prec, rows in (("dfd", 152), ("fC", 112)):
+        def one(lib):
+            c = glob.glob(os.path.join(DIR2, f"{lib}_oz2_results_{prec}_time_*.csv"))
+            assert len(c) == 1, c
+            return t.time_table(t.read_csv(c[0]))
+        ours, ref = one("ours"), one("ref")
+        n = 0
+        for key, o in ours.items():
+            if not t.is_emulation(key[1]):
+                continue
+            r = ref[key]
+            assert (o["relerr_max"], o["relerr_med"]) == (r["relerr_max"], r["relerr_med"]), (prec, key)
+            assert float(o["TFLOPS"]) > float(r["TFLOPS"]), (prec, key)
+            n += 1
+        assert n == rows
