@@ -198,7 +198,9 @@ def int8_peak(torch, seconds=2.0, S=16384):
         return {"burst": ops / (best * 1e-3) / 1e12, "sustained": ops / (sust * 1e-3) / 1e12, "unit": "TOP/s",
                 "all_ones_8192_burst": 2.0 * S1 ** 3 / (best1 * 1e-3) / 1e12,
                 "how": f"torch._int_mm (cuBLASLt s8s8s32) {S}^3 random int8, best of 10 / {reps} calls back to back ({sust * reps / 1e3:.1f} s); "
-                       "all_ones_8192_burst = the reference driver's INT8-GEMM row (GEMMul8/testing/test_double.cu:287-309), best of 10"}
+                       "all_ones_8192_burst = the same call on all-ones data at 8192^3, best of 10 (the reference driver's INT8-GEMM row, "
+                       "GEMMul8/testing/test_double.cu:287-309, calls cublasGemmEx itself and reads 3787 TOP/s on this GPU: "
+                       "profiles/r01_reference_drivers/)"}
     except Exception as e:     # no int8 path in this torch build: the caller falls back to 2 x bf16
         return {"error": str(e)[:200]}
 
