@@ -124,7 +124,8 @@ int gemmul8_b200_init(int device);
  *   "gemm_pair"  (OZ_GEMM_PAIR)  -1 auto | 0 single-CTA kernel | 1 CTA-pair kernel      "band" (OZ_BAND), "pair_band" (OZ_PAIR_BAND)
  *   "pair_stages" (OZ_PAIR_STAGES) 0 auto | 4 | 5 | 6     "encode_reference" (GEMMUL8_B200_ENCODE=reference) 0 | 1
  *   "fused_k" (GEMMUL8_B200_FUSED_K) largest k that takes the single-kernel product + CRT path (0 = never)
- *   "scale_fork" (GEMMUL8_B200_SCALE_FORK) 1 | 0: small operands are scaled on two streams side by side */
+ *   "scale_fork" (GEMMUL8_B200_SCALE_FORK) 1 | 0: small operands are scaled on two streams side by side
+ *   "tma_store" (GEMMUL8_B200_TMA_STORE) 0 | 1: residues of the pair GEMM leave through TMA bulk tensor stores */
 int gemmul8_b200_set_option(const char *name, int value);
 int gemmul8_b200_get_option(const char *name, int *value);
 

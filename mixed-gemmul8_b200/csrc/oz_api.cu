@@ -32,10 +32,11 @@ Option g_options[] = {
     {"gemm_pair", "OZ_GEMM_PAIR", {-1}, -1, 1},
     {"band", "OZ_BAND", {16}, 1, 1024},
     {"pair_band", "OZ_PAIR_BAND", {0}, 0, 4096},
-    {"pair_stages", "OZ_PAIR_STAGES", {0}, 0, 7},
+    {"pair_stages", "OZ_PAIR_STAGES", {0}, 0, 6},
     {"encode_reference", nullptr, {0}, 0, 1},
     {"fused_k", "GEMMUL8_B200_FUSED_K", {0}, 0, 1 << 17},
     {"scale_fork", "GEMMUL8_B200_SCALE_FORK", {1}, 0, 1},
+    {"tma_store", "GEMMUL8_B200_TMA_STORE", {0}, 0, 1},
 };
 std::once_flag g_options_once;
 void load_options_from_env() {
@@ -67,6 +68,7 @@ const Tuning &tuning() {
     t.encode_reference = g_options[4].value.load(std::memory_order_relaxed);
     t.fused_k          = g_options[5].value.load(std::memory_order_relaxed);
     t.scale_fork       = g_options[6].value.load(std::memory_order_relaxed);
+    t.tma_store        = g_options[7].value.load(std::memory_order_relaxed);
     return t;
 }
 }  // namespace oz

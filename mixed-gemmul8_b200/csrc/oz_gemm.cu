@@ -370,7 +370,8 @@ constexpr int PAIR_STAGE  = PAIR_SMEM_A + PAIR_SMEM_B;  // 32 KiB per CTA and st
 constexpr int PAIR_EPI_WARPS = 16;                      // 4 per TMEM lane quarter, 64 of the tile's 256 columns each
 constexpr int PAIR_THREADS   = (4 + PAIR_EPI_WARPS) * 32;
 constexpr int PAIR_SCRATCH   = 0;                       // (the epilogue needs no shared memory any more)
-constexpr int pair_smem_total(int stages) { return stages * PAIR_STAGE + SMEM_BARRIERS + PAIR_SCRATCH + 1024; }
+constexpr int PAIR_STAGE_OUT = 4 * 2 * 4096;            // TMA-store epilogue: per lane quarter two boxes of 32 columns x 128 rows
+constexpr int pair_smem_total(int stages, bool tma_store) { return stages * PAIR_STAGE + (tma_store ? PAIR_STAGE_OUT : 0) + SMEM_BARRIERS + PAIR_SCRATCH + 1024; }
 constexpr int PAIR_BAND = 8;                            // 256-row tiles per scheduling band
 
 struct PairSched {   // items = (256-row tile, column tile, modulus), ordered (band of 8 row tiles, modulus, column tile, row tile)
@@ -401,12 +402,15 @@ struct PairArgs {
     uint32_t *claims;       // with `slot`: one word per pair, zeroed before the launch
 };
 
-template <bool RMW, int NSTAGES>
+template <bool RMW, int NSTAGES, bool TMAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
-oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PairArgs args) {
+oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const PairArgs args) {
+    static_assert(!(RMW && TMAST), "the TMA-store epilogue is for plain passes");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base  = smem_base + NSTAGES * PAIR_STAGE;
+    const uint32_t stage_out = smem_base + NSTAGES * PAIR_STAGE;                       // TMAST: 32 KiB of residue staging (1024-B aligned)
+    const uint32_t bar_base  = stage_out + (TMAST ? PAIR_STAGE_OUT : 0);
     auto full_bar   = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar  = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
     auto tfull_bar  = [&](int s) { return bar_base + 8u * (2 * NSTAGES + s); };
@@ -435,6 +439,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (TMAST) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -551,20 +556,51 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             constexpr bool DRAIN_FIRST = !RMW && OZ_EPI_DRAIN_FIRST;
             uint32_t v2[DRAIN_FIRST ? NCH : 1][32];
             if constexpr (DRAIN_FIRST) {
-#ifdef OZ_DBG_NO_LDTM   // experiment builds only (tools/ab_build.sh): what bounds the epilogue?
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v2[c][e] = taddr * (e + 1) + c;
-#else
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) tmem_ld32(taddr + 32 * c, v2[c]);
                 tmem_ld_wait(v2[0], v2[1]);
-#endif
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(tempty_bar(acc), 0));
             }
+            if constexpr (TMAST) {
+                // Residues leave through the TMA: each lane quarter (4 warps = 32 columns x 256 rows of C) stages its 8 KiB in
+                // shared memory in the 128-byte-swizzled layout of two 32 x 128 boxes and ONE thread issues two bulk tensor
+                // stores.  A warp's direct store spans 32 lines (lane == column) and costs the LSU 32 wavefronts; here the
+                // LSU sees conflict-free 16-byte shared stores, the TMA writes whole 128-byte lines and clips at the edges
+                // of the matrix, so there is no bounds logic at all.
+                uint32_t pk[NCH][8];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (mj != 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v2[c][e] = reduce_mod_u((int32_t)v2[c][e], negm, inv, off);
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; ++w)
+                        pk[c][w] = __byte_perm(__byte_perm(v2[c][4 * w], v2[c][4 * w + 1], 0x0040), __byte_perm(v2[c][4 * w + 2], v2[c][4 * w + 3], 0x0040), 0x5410);
+                }
+                const bool issuer = rowgroup == 0 && lane == 0;
+                if (issuer) tma_store_wait_read();            // the previous item's boxes have been read out of shared memory
+                named_barrier(1 + q, 128);
+                // box h = rowgroup >> 1 (rows 0-127 / 128-255 of the tile); inside a box row (= one column of C, 128 bytes) this
+                // warp owns bytes 64 (rowgroup & 1) .. + 63; 16-byte chunk i of row c sits at chunk i ^ (c & 7)
+                const uint32_t box = stage_out + q * 8192 + (rowgroup >> 1) * 4096 + lane * 128;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t i0 = (rowgroup & 1) * 4 + 2 * c;
+                    st_shared_v4(box + (((i0 + 0) ^ (lane & 7)) << 4), pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+                    st_shared_v4(box + (((i0 + 1) ^ (lane & 7)) << 4), pk[c][4], pk[c][5], pk[c][6], pk[c][7]);
+                }
+                fence_proxy_async_smem();
+                named_barrier(1 + q, 128);
+                if (issuer) {
+                    const int ccol = (int)(tu * 256 + rank * 128 + q * 32), crow = (int)(tv * BLOCK_N);
+                    tma_store_3d(&map_c, stage_out + q * 8192, crow, ccol, (int)j);
+                    tma_store_3d(&map_c, stage_out + q * 8192 + 4096, crow + 128, ccol, (int)j);
+                    tma_store_commit();
+                }
+            } else {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 uint32_t vr[DRAIN_FIRST ? 1 : 32];
@@ -578,11 +614,7 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                 }
                 uint32_t (&v)[32] = *reinterpret_cast<uint32_t (*)[32]>(DRAIN_FIRST ? v2[DRAIN_FIRST ? c : 0] : vr);
-#ifdef OZ_DBG_NO_BARRETT
-                if (false) {
-#else
                 if (mj != 0) {          // (modulus 256: the low byte, which the packing below takes anyway)
-#endif
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = reduce_mod_u((int32_t)v[e], negm, inv, off);
                 }
@@ -607,11 +639,6 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                     }
                 }
-#ifdef OZ_DBG_NO_STORE
-                if (interior) {
-                    if ((pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]) == 0x12345u) *reinterpret_cast<uint32_t *>(po) = pk[0];
-                } else {
-#else
                 if (interior && vec32_ok) {
                     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(po), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                                  "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
@@ -619,15 +646,16 @@ oz_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     *reinterpret_cast<uint4 *>(po)      = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(po + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 } else {
-#endif
 #pragma unroll
                     for (int w = 0; w < 8; ++w)
                         if (row0 + 32 * c + 4 * w < args.rows_store) *reinterpret_cast<uint32_t *>(po + 4 * w) = pk[w];
                 }
             }
+            }   // !TMAST
         }
     }
 
+    if (TMAST && warp >= 4 && ((warp - 4) >> 2) == 0 && lane == 0) tma_store_wait_all();   // this thread's bulk stores have landed
     tcgen05_fence_before();
     cluster_sync_all();          // nobody frees tensor memory while the peer may still use the pair's resources
     if (warp == 2) {
@@ -695,6 +723,18 @@ bool make_operand_map(CUtensorMap *map, const int8_t *base, size_t ld8i, size_t 
     cuuint32_t estr[3]    = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+bool make_residue_map(CUtensorMap *map, const uint8_t *base, size_t ld, size_t rows, size_t cols, size_t slices, size_t slice_stride) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3]    = {(cuuint64_t)rows, (cuuint64_t)cols, (cuuint64_t)slices};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)slice_stride};
+    cuuint32_t box[3]     = {128, 32, 1};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -864,9 +904,23 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     a.sched.init((uint32_t)((p.rowsB + 255) / 256), (uint32_t)((p.rowsA + BLOCK_N - 1) / BLOCK_N), p.num_slices, band);
     a.C8u = p.C8u; a.ldc8u = p.ldc8u; a.sizeC = p.sizeC;
     a.combine = p.combine; a.C8u_aux = p.C8u_aux ? p.C8u_aux : p.C8u;
-    const int stages = tn.pair_stages ? tn.pair_stages : p.share_sm ? 4 : PAIR_STAGES;   // (7 fit too: no measurable difference)
-    auto kern = stages == 4 ? oz_gemm_pair_kernel<RMW, 4> : stages == 5 ? oz_gemm_pair_kernel<RMW, 5> : stages == 7 ? oz_gemm_pair_kernel<RMW, 7> : oz_gemm_pair_kernel<RMW, 6>;
-    const int smem_bytes = pair_smem_total(stages == 4 ? 4 : stages == 5 ? 5 : stages == 7 ? 7 : 6);
+    int stages = tn.pair_stages ? tn.pair_stages : p.share_sm ? 4 : PAIR_STAGES;   // (7 fit too: no measurable difference)
+    if (stages != 4 && stages != 5) stages = 6;
+    // TMA-store epilogue (option tma_store, default off): plain passes whose residue matrix has 16-byte-multiple strides (TMA's
+    // requirement).  Measured equal to the 256-bit direct stores from k = 512 to 16384 (profiles/r02_ab_tma_store.jsonl: the
+    // stores are not what bounds the short-k kernel), so the path with fewer moving parts stays the default.
+    CUtensorMap mc{};
+    bool tma_store = !RMW && tn.tma_store != 0 && (p.ldc8u % 16) == 0 && (p.sizeC % 16) == 0 && (reinterpret_cast<uintptr_t>(p.C8u) % 16) == 0;
+    if (tma_store) tma_store = detail::make_residue_map(&mc, p.C8u, p.ldc8u, a.rows_store, p.rowsB, p.num_slices, p.sizeC);
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, PairArgs);
+    if constexpr (RMW) {
+        kern = stages == 4 ? oz_gemm_pair_kernel<true, 4, false> : stages == 5 ? oz_gemm_pair_kernel<true, 5, false> : oz_gemm_pair_kernel<true, 6, false>;
+    } else if (tma_store) {
+        kern = stages == 4 ? oz_gemm_pair_kernel<false, 4, true> : stages == 5 ? oz_gemm_pair_kernel<false, 5, true> : oz_gemm_pair_kernel<false, 6, true>;
+    } else {
+        kern = stages == 4 ? oz_gemm_pair_kernel<false, 4, false> : stages == 5 ? oz_gemm_pair_kernel<false, 5, false> : oz_gemm_pair_kernel<false, 6, false>;
+    }
+    const int smem_bytes = pair_smem_total(stages, tma_store);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const uint32_t max_pairs = (uint32_t)sm_count() / 2;
@@ -879,7 +933,7 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
         e = cudaMemsetAsync(p.claims, 0, sizeof(uint32_t) * max_pairs, st);
         if (e != cudaSuccess) return e;
     }
-    kern<<<2 * pairs, PAIR_THREADS, smem_bytes, st>>>(ma, mb, a);   // cluster dims (2,1,1) are a kernel attribute
+    kern<<<2 * pairs, PAIR_THREADS, smem_bytes, st>>>(ma, mb, mc, a);   // cluster dims (2,1,1) are a kernel attribute
     count_launch();
     return cudaGetLastError();
 }

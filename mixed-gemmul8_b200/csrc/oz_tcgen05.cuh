@@ -68,6 +68,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// TMA store of a shared-memory box (this CTA's) into a 3-D tensor, bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes done
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -229,6 +242,8 @@ __device__ __forceinline__ uint32_t claim_pair_slot(const uint32_t *slot, uint32
 // host helpers defined in oz_gemm.cu
 namespace detail {
 bool make_operand_map(CUtensorMap *map, const int8_t *base, size_t ld8i, size_t rows, size_t slices, size_t slice_stride, uint32_t box_rows);
+// (row, column, modulus) view of a stack of column-major uint8 residue matrices; box = 128 rows x 32 columns, 128-byte swizzle
+bool make_residue_map(CUtensorMap *map, const uint8_t *base, size_t ld, size_t rows, size_t cols, size_t slices, size_t slice_stride);
 int sm_count();                                        // of the current device (cached)
 const uint32_t *placement_slots(bool allow_probe);     // smid -> block index of a plain launch, or nullptr
 bool stream_is_capturing(cudaStream_t st);

@@ -623,3 +623,19 @@ def test_fused_path_is_selected_by_k(g):
         g.set_option("fused_k", old)
     assert torch.equal(C_f, C_u) and torch.equal(C_2, C_u) and torch.equal(C_a, C_b)
     assert v_u["C8u"].any() and not v_f["C8u"].any() and v_2["C8u"].any()
+
+
+def test_tma_store_epilogue_equals_direct_stores(g):
+    """Option "tma_store": the pair GEMM's residues staged in shared memory (128-byte swizzle) and written by TMA bulk tensor
+    stores, against the default direct 256-bit stores: residues and C byte for byte, ragged edges included (the TMA clips)."""
+    torch = torch_()
+    try:
+        for (m, n, k, N) in [(2048, 2304, 512, 14), (1040, 4100, 300, 9), (4096, 1000, 1024, 20)]:     # m % 16 == 0: TMA strides
+            A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=8)
+            g.set_option("tma_store", 0)
+            C0, v0 = run_ours(g, m, n, k, N, True, A, B)
+            g.set_option("tma_store", 1)
+            C1, v1 = run_ours(g, m, n, k, N, True, A, B)
+            assert torch.equal(v0["C8u"], v1["C8u"]) and torch.equal(C0, C1) and C0.abs().sum().item() > 0
+    finally:
+        g.set_option("tma_store", 0)
