@@ -1,5 +1,5 @@
 // An application that knows nothing about this repository: plain cuBLAS calls (column-major, host
-// alpha / beta).  tests/test_interposer.py runs it with and without
+// alpha / beta, and one call in CUBLAS_POINTER_MODE_DEVICE).  tests/test_interposer.py runs it with and without
 // LD_PRELOAD=libgemmul8_b200_blas.so and compares the printed samples of C.
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
@@ -51,6 +51,24 @@ int main() {
         cudaStreamSynchronize(st);
         cudaMemcpy(C.data(), dC, C.size() * 16, cudaMemcpyDeviceToHost);
         for (size_t i = 0; i < C.size(); i += 39989) printf("Z %zu %.17g %.17g\n", i, C[i].x, C[i].y);
+    }
+    {   // DGEMM with alpha / beta in DEVICE memory (CUBLAS_POINTER_MODE_DEVICE), C = -2 A^T B + 0.25 C
+        const int m = 768, n = 1024, k = 2048;
+        std::vector<double> A((size_t)k * m), B((size_t)k * n), C((size_t)m * n);
+        fill(A, 6); fill(B, 7); fill(C, 8);
+        double *dA, *dB, *dC, *dS;
+        cudaMalloc(&dA, A.size() * 8); cudaMalloc(&dB, B.size() * 8); cudaMalloc(&dC, C.size() * 8); cudaMalloc(&dS, 16);
+        cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, B.data(), B.size() * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(dC, C.data(), C.size() * 8, cudaMemcpyHostToDevice);
+        const double scal[2] = {-2.0, 0.25};
+        cudaMemcpy(dS, scal, 16, cudaMemcpyHostToDevice);
+        cublasSetPointerMode(h, CUBLAS_POINTER_MODE_DEVICE);
+        cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, m, n, k, dS, dA, k, dB, k, dS + 1, dC, m);
+        cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(C.data(), dC, C.size() * 8, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < C.size(); i += 99991) printf("P %zu %.17g\n", i, C[i]);
     }
     {   // a tiny DGEMM that must stay with cuBLAS (below GEMMUL8_MIN_MNK)
         const int m = 8, n = 8, k = 8;

@@ -31,7 +31,7 @@ def parse(text):
     vals = {}
     for line in text.splitlines():
         f = line.split()
-        if f and f[0] in "DZT":
+        if f and f[0] in "DZTP":
             vals[(f[0], f[1])] = [float(x) for x in f[2:]]
     return vals
 
@@ -49,7 +49,9 @@ def test_unmodified_cublas_application_is_emulated():
         for x, y in zip(a[key], b[key]):
             assert abs(x - y) <= 1e-10 * max(1.0, abs(x)), (key, x, y)       # 14 moduli: ~1e-13 relative
     lines = [l for l in pre.stderr.splitlines() if l.startswith("gemmul8_b200_blas:")]
-    assert len(lines) == 2 and "1024 x 768 x 2048" in lines[0] and "512 x 384 x 1024" in lines[1]   # the 8^3 call stayed with cuBLAS
+    # the 8^3 call stayed with cuBLAS; the call in CUBLAS_POINTER_MODE_DEVICE is emulated too (alpha / beta read on the device)
+    assert len(lines) == 3 and "1024 x 768 x 2048" in lines[0] and "512 x 384 x 1024" in lines[1] and "768 x 1024 x 2048" in lines[2]
+    assert any(k[0] == "P" for k in a)
     assert a[("T", "0")] == b[("T", "0")] == [16.0]
 
 
@@ -62,6 +64,6 @@ def test_interposer_takes_the_low_memory_call_when_the_workspace_is_capped():
     full = subprocess.run([APP], capture_output=True, text=True, env=base, check=True)
     capped = subprocess.run([APP], capture_output=True, text=True, env=dict(base, GEMMUL8_MAX_WORK_MB="24"), check=True)
     a, b = parse(full.stdout), parse(capped.stdout)
-    assert [v for k, v in a.items() if k[0] == "D"] == [v for k, v in b.items() if k[0] == "D"]      # bit-identical
+    assert [v for k, v in a.items() if k[0] in "DP"] == [v for k, v in b.items() if k[0] in "DP"]      # bit-identical
     lines = [l for l in capped.stderr.splitlines() if l.startswith("gemmul8_b200_blas:")]
-    assert len(lines) == 1 and "1024 x 768 x 2048" in lines[0] and "low-memory blocks" in lines[0]
+    assert len(lines) == 2 and "1024 x 768 x 2048" in lines[0] and all("low-memory blocks" in l for l in lines)
