@@ -639,3 +639,59 @@ def test_tma_store_epilogue_equals_direct_stores(g):
             assert torch.equal(v0["C8u"], v1["C8u"]) and torch.equal(C0, C1) and C0.abs().sum().item() > 0
     finally:
         g.set_option("tma_store", 0)
+
+
+def test_no_writes_outside_workspace_and_c_on_the_round2_paths(g):
+    """(compute-sanitizer is closed on this pool.)  Guard bands around `work` and C for the paths added in round 2: the placed
+    pair kernel with its claim table and 256-bit stores, ragged edges (predicated 4-byte stores), the TMA-store epilogue
+    (clipped by the tensor map), the single-kernel product + CRT, and a sub-block product in the middle of a larger matrix."""
+    torch = torch_()
+
+    def guarded(nbytes, pad=1 << 16):
+        buf = torch.full((nbytes + 2 * pad,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = pad + (-(buf.data_ptr() + pad)) % 256
+        return buf, buf[off:off + nbytes], off
+
+    def intact(buf, off, nbytes):
+        return bool((buf[:off] == 0xA5).all()) and bool((buf[off + nbytes:] == 0xA5).all())
+
+    cases = [(2048, 2304, 384, 14, {}), (1040, 1100, 300, 9, {}), (2048, 2304, 384, 14, {"tma_store": 1}), (1040, 1100, 300, 9, {"tma_store": 1}),
+             (777, 1301, 300, 14, {"fused_k": 4096}), (2049, 2305, 130, 20, {})]
+    try:
+        for (m, n, k, N, opts) in cases:
+            for name, val in opts.items():
+                g.set_option(name, val)
+            A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=21)
+            ws = g.workSize(m, n, k, N)
+            wbuf, work, woff = guarded(ws)
+            cbuf, cbytes, coff = guarded(m * n * 8)
+            C = cbytes.view(torch.float64).view(n, m)
+            g.gemm(None, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work)
+            torch.cuda.synchronize()
+            assert intact(wbuf, woff, ws) and intact(cbuf, coff, m * n * 8), (m, n, k, N, opts)
+            Cr, _ = run_ours(g, m, n, k, N, True, A, B)
+            assert torch.equal(C, Cr)
+            for name in opts:
+                g.set_option(name, 0)
+        # a product restricted to an interior block must leave the rest of C and of the residue matrix alone
+        m, n, k, N = 1536, 1280, 256, 14
+        A, B = operands(g, m, n, k, 0, 0, torch.float64, torch.float64, seedB=22)
+        work = torch.zeros(g.workSize(m, n, k, N), dtype=torch.uint8, device="cuda")
+        C = torch.full((n, m), 7.0, dtype=torch.float64, device="cuda")
+        args = g.make_args(0, 0, m, n, k, 1.0, A, m, B, k, 0.0, C, m, N, True, work)
+        g.gemm_part(args, g.PART_SCALE_A, 0, m, 0, 0)
+        g.gemm_part(args, g.PART_SCALE_B, 0, 0, 0, n)
+        g.gemm_part(args, g.PART_PRODUCT, 512, 1024, 256, 768)
+        torch.cuda.synchronize()
+        Cf, vf = run_ours(g, m, n, k, N, True, A, B)
+        inside = torch.zeros((n, m), dtype=torch.bool, device="cuda")
+        inside[256:768, 512:1024] = True
+        assert torch.equal(C[inside], Cf[inside]) and bool((C[~inside] == 7.0).all())
+        v = g.work_views(work, g.work_layout(m, n, k, N), N, m, n)
+        assert torch.equal(v["C8u"][:, 256:768, 512:1024], vf["C8u"][:, 256:768, 512:1024])
+        outside = v["C8u"].clone()
+        outside[:, 256:768, 512:1024] = 0
+        assert not outside.any()
+    finally:
+        for name in ("tma_store", "fused_k"):
+            g.set_option(name, 0)

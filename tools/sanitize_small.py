@@ -30,4 +30,15 @@ for ct in (1, 2, 3):
     cplx(70, 52, 100, 8, False, 1, 0, torch.complex64, ct)
 g.set_option("gemm_pair", 1)
 real(300, 520, 260, 14, True, 0, 0, torch.float64)
+real(2048, 2304, 384, 14, True, 0, 0, torch.float64)          # >= 74 pairs' worth of items: placed path with the claim table, 256-bit stores
+real(1040, 1100, 300, 9, True, 0, 0, torch.float64)           # ragged edges: predicated 4-byte stores
+g.set_option("tma_store", 1)
+real(2048, 2304, 384, 14, True, 0, 0, torch.float64)          # TMA-store epilogue, interior
+real(1040, 1100, 300, 9, True, 0, 0, torch.float64)           # ... clipped at the edges of the matrix
+g.set_option("tma_store", 0)
+g.set_option("fused_k", 4096)
+real(777, 1301, 300, 14, True, 0, 0, torch.float64)           # single-kernel product + CRT, ragged
+real(300, 260, 200, 6, True, 0, 0, torch.float32)
+g.set_option("fused_k", 0)
+cplx(700, 600, 320, 14, True, 0, 0, torch.complex128, 3)      # Karatsuba: the combine passes of the pair kernel
 print("sanitize workload done")
