@@ -544,9 +544,26 @@ int gemm_complex(gemmul8_b200_args *a) {
         OZ_CUDA(product(A_re, B_im, C_im, oz::RC_ADD, nullptr), "Ar Bi");
     } else {  // Karatsuba: E = ArBr, F = AiBi, G = (Ar+Ai)(Br+Bi); Re = E - F, Im = G - (E + F)
         OZ_CUDA(product(A_re, B_re, C_re, oz::RC_STORE, nullptr), "E");
-        OZ_CUDA(product(A_im, B_im, C_re, oz::RC_KARATSUBA_F, C_im), "F");
-        OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeA, A_re, A_im, st), "Ar + Ai");   // in place, as the reference (gemmul8.cu:853-855)
-        OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeB, B_re, B_im, st), "Br + Bi");
+        // The in-place slice sums Ar <- Ar + Ai, Br <- Br + Bi (as the reference, gemmul8.cu:853-855) only need E to be done: Ar
+        // and Br are not read by F, Ai and Bi are only READ by both.  They are HBM-bound (5.6 GB at 8192^3), F is tensor-bound:
+        // on a side stream they run beside F (which then leaves room on the SMs: 4 pipeline stages) instead of after it.
+        const bool overlap = oz::tuning().scale_fork != 0 && g_side.init();
+        if (overlap) {
+            SideStreams &S = g_side;
+            OZ_CUDA(cudaEventRecord(S.start, st), "event record");
+            OZ_CUDA(cudaStreamWaitEvent(S.sB, S.start, 0), "stream wait");
+            OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeA, A_re, A_im, S.sB), "Ar + Ai");
+            OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeB, B_re, B_im, S.sB), "Br + Bi");
+            OZ_CUDA(cudaEventRecord(S.done, S.sB), "event record");
+            gp.share_sm = true;
+            OZ_CUDA(product(A_im, B_im, C_re, oz::RC_KARATSUBA_F, C_im), "F");
+            gp.share_sm = false;
+            OZ_CUDA(cudaStreamWaitEvent(st, S.done, 0), "stream wait");
+        } else {
+            OZ_CUDA(product(A_im, B_im, C_re, oz::RC_KARATSUBA_F, C_im), "F");
+            OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeA, A_re, A_im, st), "Ar + Ai");
+            OZ_CUDA(oz::launch_add_int8_slices(N, L.sizeB, B_re, B_im, st), "Br + Bi");
+        }
         OZ_CUDA(product(A_re, B_re, C_im, oz::RC_RSUB, nullptr), "G");
     }
     timer.mark();
