@@ -6,18 +6,22 @@
 // by ONE persistent kernel: the int32 product lives only in tensor memory; HBM sees the int8 slices
 // coming in (TMA, 128-byte swizzle) and one uint8 residue per element and modulus going out.
 //
-// Kernel anatomy (one CTA per SM, 256 threads):
-//   warp 0      TMA producer: 4-stage ring of {A tile 128 x 128 B, B tile 256 x 128 B}
-//   warp 1      MMA issuer  : tcgen05.mma.cta_group::1.kind::i8, M=128, N=256, K=32 per instruction,
-//                             accumulators double-buffered in TMEM (2 x 256 columns)
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue    : tcgen05.ld (lane == row), Barrett reduction mod m_j, 32 x 16 byte transpose
-//                             through a padded smem scratch, then 4-byte stores (4 rows of one column);
-//                             complex passes first combine with the stored residue (ResidueCombine),
-//                             whose words were prefetched before the accumulator became ready
-//   warps 8-11  epilogue too (columns 128-255 of the tile; warps 4-7 then take columns 0-127)
-// A work item is (C tile, modulus), ordered (band of 16 row tiles, modulus, column tile, row tile): the ~148 items in
-// flight share one modulus and a compact block of panels.  (The single-kernel product + CRT lives in oz_gemm_crt.cu.)
+// Two kernels share this file:
+//   oz_gemm_pair_kernel    (default)  two CTAs of a TPC share a 256 x 256 tile (tcgen05.mma.cta_group::2); see the banner
+//                                     in front of it.  EPI_RESIDUE with every combine mode.
+//   oz_gemm_tcgen05_kernel            one CTA per SM, 384 threads, M 128 x N 256 tiles: the raw-int32 tap (EPI_INT32), the
+//                                     accurate-mode bound product (EPI_ABSMAX), and EPI_RESIDUE where the pair kernel is
+//                                     switched off (option gemm_pair = 0) or no placement table exists:
+//     warp 0      TMA producer: 4-stage ring of {A tile 128 x 128 B, B tile 256 x 128 B}
+//     warp 1      MMA issuer  : tcgen05.mma.cta_group::1.kind::i8, M=128, N=256, K=32 per instruction,
+//                               accumulators double-buffered in TMEM (2 x 256 columns)
+//     warp 2      TMEM allocator
+//     warps 4-11  epilogue    : tcgen05.ld (lane == row of C), Barrett reduction mod m_j, 32 x 16 byte transpose through a
+//                               padded smem scratch, 4-byte stores (4 rows of one column); warps 4-7 columns 0-127 of the
+//                               tile, warps 8-11 columns 128-255; complex passes first combine with the stored residue
+//                               (ResidueCombine), whose words were prefetched before the accumulator became ready
+// A work item is (C tile, modulus), ordered (band of tiles, modulus, ...): the items in flight share one modulus and a
+// compact block of panels.  (The single-kernel product + CRT lives in oz_gemm_crt.cu.)
 //
 // Both operands are K-major exactly as the reference lays them out (A8i[j][row][k], B8i[j][col][k],
 // row stride lda8i), so a 3-D tensor map (k, row, modulus) serves all moduli and K / row tails are
@@ -342,17 +346,20 @@ oz_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
 // =============================================================================================
 // CTA-pair variant (tcgen05 cta_group::2) of the residue kernel: two CTAs on the SMs of one TPC share
-// a 256 x 256 tile.  Each CTA keeps its own 128 rows of A and HALF of the B tile (128 columns) in
-// shared memory; the tensor cores of the pair exchange the B halves, so per 256 x 256 x 128 block of
+// a 256 x 256 tile.  Each CTA keeps 128 rows of the "M-side" operand and HALF of the "N-side" tile (128 rows) in
+// shared memory; the tensor cores of the pair exchange the halves, so per 256 x 256 x 128 block of
 // MACs the pair pulls 64 KB through L2 instead of the 96 KB two independent CTAs need.  The kernel
 // is power-bound on B200, and the saved traffic turns into clock -- PROVIDED the pairs are placed like
-// the CTAs of a plain launch (see `placement_slots`): DESIGN.md 3.4.
-//   every CTA    warp 0 : TMA producer of its own A rows and B half; the bytes are accounted on the
+// the CTAs of a plain launch (see `placement_slots` and the claim table): DESIGN.md 3.2.
+// The operand ROLES ARE SWAPPED with respect to C = A B: the M side walks rows of B8i (columns of C), the N side rows of
+// A8i (rows of C), so that a lane of the epilogue holds consecutive ROWS of one column of the column-major residue matrix.
+//   every CTA    warp 0 : TMA producer of its 128 M-side rows and its N-side half; the bytes are accounted on the
 //                         LEADER's full barrier (cp.async.bulk.tensor .cta_group::2)
-//   leader only  warp 1 : issues tcgen05.mma.cta_group::2 (M 256, N 256, K 32); its commits are
-//                         multicast to the empty / accumulator-full barriers of both CTAs
-//   every CTA    warp 2 : TMEM allocation (cta_group::2), warps 4-11: epilogue of its own 128 rows;
-//                         one lane per warp tells the leader that the accumulator buffer is drained
+//   leader only  warp 1 : claims the pair's work slot, issues tcgen05.mma.cta_group::2 (M 256, N 256, K 32); its commits
+//                         are multicast to the empty / accumulator-full barriers of both CTAs
+//   every CTA    warp 2 : TMEM allocation (cta_group::2)
+//   every CTA    warps 4-19 : epilogue of its own 128 columns of C: tcgen05.ld.x32, Barrett, pack, 256-bit stores (or TMA
+//                         bulk stores, option tma_store); one lane per warp tells the leader that the buffer is drained
 // =============================================================================================
 #ifndef OZ_EPI_DRAIN_FIRST
 #define OZ_EPI_DRAIN_FIRST 1   // A/B knob of tools/ab_build.sh; 0 = read and reduce the slab in two halves
