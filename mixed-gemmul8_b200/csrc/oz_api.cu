@@ -384,6 +384,13 @@ int gemm_real(gemmul8_b200_args *a) {
     PhaseTimer timer(a->flags, st);
     timer.mark();
 
+    // the pair GEMM's claim table is zeroed here, in front of the scaling kernels, so that no memset node sits between the
+    // last encoder and the product (small problems are launch-latency-bound); fast mode only: the accurate-mode bound
+    // product runs in between on the single-CTA kernel, which does not use the table, but keep that path plain
+    uint32_t *claims = claims_of(work, L);
+    const bool claims_early = claims != nullptr && a->fastmode && !(a->flags & GEMMUL8_FLAG_ONLY_SCALE_A);
+    if (claims_early) OZ_CUDA(cudaMemsetAsync(claims, 0, oz::kClaimBytes, st), "memset claim table");
+
     // ---------------- phase 0: scaling ----------------
     if (a->fastmode) {
         const float l2 = oz::host_tab::OZ_LOG2M_FAST[ti];
@@ -450,7 +457,8 @@ int gemm_real(gemmul8_b200_args *a) {
     const bool split = oz::host_tab::OZ_M_LO[ti] != 0.0 && a->dtype_C == GEMMUL8_F64;  // numM == 2 (N >= 8) and fp64 out
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.B8i = B8i; gp.rowsA = m; gp.rowsB = n; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB;
-    gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
+    gp.num_slices = N; gp.first_modulus = 0; gp.C8u = C8u; gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims;
+    gp.claims_zeroed = claims_early;
     int rc = block_to_c(a, gp, take_fused(a), split, a->C, sftA, sftB, st, &timer);
     if (rc) return rc;
     timer.finish(a->timers_ns);

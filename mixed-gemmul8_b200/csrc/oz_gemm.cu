@@ -936,7 +936,7 @@ cudaError_t launch_pair(const GemmProblem &p, cudaStream_t st) {
     static_assert(kClaimBytes >= sizeof(uint32_t) * 128, "claim table: one word per pair");
     a.slot = (pairs == max_pairs && p.claims != nullptr && max_pairs <= kClaimBytes / sizeof(uint32_t)) ? placement_slots(false) : nullptr;
     a.claims = p.claims;
-    if (a.slot != nullptr) {
+    if (a.slot != nullptr && !p.claims_zeroed) {
         e = cudaMemsetAsync(p.claims, 0, sizeof(uint32_t) * max_pairs, st);
         if (e != cudaSuccess) return e;
     }

@@ -271,7 +271,7 @@ cudaError_t launch_fused(const GemmProblem &p, cudaStream_t st) {
     a.slot = (pairs == max_pairs && p.claims != nullptr && max_pairs <= kClaimBytes / sizeof(uint32_t))
                  ? detail::placement_slots(!detail::stream_is_capturing(st)) : nullptr;
     a.claims = p.claims;
-    if (a.slot != nullptr) {
+    if (a.slot != nullptr && !p.claims_zeroed) {
         e = cudaMemsetAsync(p.claims, 0, sizeof(uint32_t) * max_pairs, st);
         if (e != cudaSuccess) return e;
     }

@@ -86,10 +86,10 @@ def test_round2_drivers_accuracy_tables_identical_between_libraries():
 
 
 def test_round2_drivers_timing_rows_carry_identical_errors_and_are_faster():
-    """flops_check of test_mixed_double and test_float_complex (sizes 1024 .. 8192, 2 .. 20 moduli, fast and accurate): every
+    """flops_check of test_mixed_double, test_mixed_float and test_float_complex (sizes 1024 .. 8192, 2 .. 20 moduli, fast and accurate): every
     emulation row has the same relerr_max / relerr_med strings with both libraries, and this library is the faster one."""
     t = _tool()
-    for prec, rows in (("dfd", 152), ("fC", 112)):
+    for prec, rows in (("dfd", 152), ("dff", 112), ("fC", 112)):
         def one(lib):
             c = glob.glob(os.path.join(DIR2, f"{lib}_oz2_results_{prec}_time_*.csv"))
             assert len(c) == 1, c
