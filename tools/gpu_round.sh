@@ -1,9 +1,5 @@
 #!/bin/bash
-# One GPU visit: parity tests, then the bench (both arms).  Outputs under gpurun_out/.
-set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > gpurun_out/gpu.txt
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench exit $?"
-cat gpurun_out/bench_ours.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu_w.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02_pytest_gpu_w.log
+tail -4 gpurun_out/r02_pytest_gpu_w.log
+timeout 300 python tools/small_sizes.py --sizes 512,1024,2048,4096 2>&1 | tee gpurun_out/r02_small_sizes_w.jsonl
