@@ -56,7 +56,9 @@ enum {
     GEMMUL8_FLAG_TIMERS = 1u, /* bracket the 4 phases with CUDA events and fill timers_ns (synchronises) */
     GEMMUL8_FLAG_STAGE_SCALING  = 1u << 4, /* run only phase 0: shifts + residue slices (parity tests) */
     GEMMUL8_FLAG_STAGE_RESIDUES = 1u << 5, /* run phases 0-2: ... + per-modulus products mod m_j      */
-    GEMMUL8_FLAG_FUSED_CRT      = 1u << 6, /* one kernel for GEMM + residues + CRT (tile-major schedule) */
+    GEMMUL8_FLAG_FUSED_CRT      = 1u << 6, /* real types: product, residue reduction, CRT, inverse scaling and alpha / beta in ONE kernel
+                                               (CRT accumulators in registers across the modulus walk; no residue matrix in HBM).
+                                               Same bits of C; measured slower than the two kernels on B200, see DESIGN.md 3.4 */
     GEMMUL8_FLAG_GEMM_SIMT      = 1u << 8, /* debug: use the CUDA-core int8 GEMM instead of tcgen05   */
     GEMMUL8_FLAG_HOST_SERIAL    = 1u << 9, /* gemm_host: copy in, compute, copy out in series (no wavefront) */
     GEMMUL8_FLAG_STRIPS         = 1u << 10, /* gemm: column-strip pipeline on three streams (measured slower) */
