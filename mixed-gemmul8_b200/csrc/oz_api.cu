@@ -973,17 +973,18 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
 
 }  // extern "C"
 
-// Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C (S <= 12, blocks shrinking towards the end).  The H2D
+// Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C (S <= 14, blocks shrinking towards the end).  The H2D
 // stream brings A row blocks and B column blocks alternately (A0, B0, A1, B1, ...); as soon as block
 // pair s is on the device the compute stream scales / encodes it and multiplies everything that has
 // become computable -- the column strip (rows 0..s, column block s) and the row strip (row block s,
 // column blocks 0..s-1) -- and the D2H stream returns each finished strip of C while the next blocks
 // are still arriving.  PCIe is full duplex, so the call ends about one strip after the last input
 // byte instead of after (inputs + compute + output) in series.
-// Measured at 16384^3 (PCIe: 55.6 GB/s H2D, 57.2 GB/s D2H, 2-D block copies as fast as contiguous ones,
-// tools/pcie_2d.py): 96 - 98 ms against a floor of 77 ms for the 4.3 GB of input; uniform or shrinking
-// blocks make no difference, and "all of B, then A in 16 row strips" is slower (105 ms: products can only
-// start once B is complete, and 1024-row strips run the GEMM ~25 % below its full-size rate).
+// Measured at 16384^3 (PCIe: 55.6 GB/s H2D, 57.2 GB/s D2H alone, ~53 / ~45 GB/s when both run; strided block copies as fast as
+// contiguous ones down to 4 KB runs, tools/pcie_d2h_width.py): 91 - 92 ms.  The last input byte lands at ~81 ms, the last
+// product ends ~5 ms later (2 ms of backlog from the compute-bound end of the wavefront + the last pair's own strips) and the
+// D2H queue drains ~4.5 ms after that (profiles/r02_e2e_timeline.txt).  "All of B, then A in 16 row strips" is slower
+// (105 ms: products can only start once B is complete).
 static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     const size_t m = h->m, n = h->n, k = h->k;
     const unsigned N = h->num_moduli, ti = N - 2;
@@ -1007,15 +1008,17 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
     const bool split     = oz::host_tab::OZ_M_LO[ti] != 0.0 && h->dtype_C == GEMMUL8_F64;
 
-    // Block boundaries: multiples of 256 rows / columns (whole GEMM tiles), at most 12 blocks per side, SHRINKING towards the
-    // end (weights 3 3 3 3 2 2 2 2 1 1 1 1): what is left to do when the last input byte has arrived -- the products with the
-    // last block pair and the D2H of their strips of C -- is proportional to the last block's share (1/24 instead of the 1/8
-    // of eight equal blocks), while the early blocks stay large enough for the GEMM to run at its full-size rate.
-    constexpr int kMaxBlocks = 12;
+    // Block boundaries: multiples of 256 rows / columns (whole GEMM tiles), SHRINKING towards the end.  The work a block pair
+    // enables grows with everything that arrived before it, so the call is transfer-bound at first and compute-bound near the
+    // end: what is left when the last input byte has arrived is the backlog plus the last pair's own strips (products and the
+    // D2H of their part of C), proportional to the last block's share.  Timeline measured at 16384^3 (profiles/
+    // r02_e2e_timeline.txt): 12 blocks ending in 1/24 shares 93.0 ms, 14 blocks ending in 1/32 shares 90.9 ms, 18 blocks ending in
+    // 1/64 shares no better (the tail is then the D2H queue, not the last strips).
+    constexpr int kMaxBlocks = 14, kShareSum = 32;
+    static const int weight[kMaxBlocks] = {4, 4, 4, 4, 3, 3, 2, 2, 1, 1, 1, 1, 1, 1};
     auto bounds = [](size_t len, size_t *b) -> int {
-        static const int weight[kMaxBlocks] = {3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1};
         const size_t tiles = (len + 255) / 256;
-        if (tiles < 24) {                       // small problems: equal blocks, at most 8
+        if (tiles < (size_t)kShareSum) {        // small problems: equal blocks, at most 8
             const int S = (int)(tiles < 8 ? (tiles ? tiles : 1) : 8);
             for (int i = 0; i <= S; ++i) { size_t x = (tiles * i / S) * 256; b[i] = x < len ? x : len; }
             b[S] = len;
@@ -1025,7 +1028,7 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
         b[0] = 0;
         for (int i = 0; i < kMaxBlocks; ++i) {
             acc += (size_t)weight[i];
-            size_t x = (tiles * acc / 24) * 256;
+            size_t x = (tiles * acc / kShareSum) * 256;
             b[i + 1] = x < len ? x : len;
         }
         b[kMaxBlocks] = len;
