@@ -321,6 +321,7 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
     const bool copy = g->exchange == GEMMUL8_MP_EXCHANGE_COPY && g->nranks > 1;
     const bool pipelined = a->fastmode != 0 && k > 0 && !cplx;   // the block-wise entry is real-only; complex: whole panels, one call
     const uint32_t epoch = ++g->epoch;
+    const bool own_b_in_place = copy && pipelined && P > 1;
 
     // full-problem argument block of this rank's C block (panels: grid buffers, or the caller's slices where nothing is exchanged)
     gemmul8_b200_args ga{};
@@ -398,9 +399,12 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
                 MP_CUDA(cudaEventRecord(g->ev_pb[pp], xs), "event record");
             }
         }
-        MP_CUDA(cudaMemcpy2DAsync(g->b_buf + off, k * esB, src, a->ldb * esB, k * esB, w, cudaMemcpyDeviceToDevice, g->xb), "own B block");
+        // my own block: read in place from b_slice by the pipelined COPY path (no local copy: 2 x the block of HBM traffic
+        // saved while the encoders compete with the incoming pushes); otherwise it joins the panel buffer
+        if (!own_b_in_place)
+            MP_CUDA(cudaMemcpy2DAsync(g->b_buf + off, k * esB, src, a->ldb * esB, k * esB, w, cudaMemcpyDeviceToDevice, g->xb), "own B block");
         if (copy) {
-            MP_CUDA(cudaEventRecord(g->ev_b[g->p], g->xb), "event record");
+            if (!own_b_in_place) MP_CUDA(cudaEventRecord(g->ev_b[g->p], g->xb), "event record");
         } else {
             for (size_t pp = 0; pp < P; ++pp) {
                 uint8_t *blk = g->b_buf + pp * w * k * esB;
@@ -420,7 +424,7 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
         return GEMMUL8_OK;
     };
     auto b_ready = [&](size_t pp) -> int {
-        if (P == 1) return GEMMUL8_OK;
+        if (P == 1 || (own_b_in_place && (int)pp == g->p)) return GEMMUL8_OK;
         if (copy && (int)pp != g->p) return wait_flag(g->flags, gemmul8_b200_grid::F_B + (int)pp, epoch, st);
         MP_CUDA(cudaStreamWaitEvent(st, g->ev_b[pp], 0), "stream wait");
         return GEMMUL8_OK;
@@ -455,6 +459,19 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
             for (int t = 0; t < 4; ++t) a->timers_ns[t] += pa.timers_ns[t];
             return rc2;
         };
+        // one column block of B: wait for it, encode it
+        auto scale_b_block = [&](gemmul8_b200_args pa, size_t pp) -> int {
+            int rc2;
+            if ((rc2 = b_ready(pp))) return rc2;
+            const size_t c0 = P > 1 ? pp * w : 0, c1 = P > 1 ? (pp + 1) * w : n_loc;
+            if (own_b_in_place && (int)pp == g->p) {   // "column c of the panel" (c0 <= c < c1) is column c - c0 of b_slice
+                pa.ldb = a->ldb;
+                pa.B   = static_cast<const uint8_t *>(a->b_slice) - c0 * a->ldb * esB;
+            }
+            if ((rc2 = part(pa, GEMMUL8_PART_SCALE_B, 0, 0, c0, c1, "scale B block"))) return rc2;
+            ++b_scaled;
+            return maybe_ack();
+        };
         for (int i = 0; i < npieces; ++i) {
             const size_t r0 = rb[i], r1 = rb[i + 1];
             gemmul8_b200_args pa = ga;
@@ -462,6 +479,9 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
                 pa.lda = r1 - r0;
                 pa.A   = g->a_buf + r0 * k * esA - r0 * esA;
             }
+            // my own B block needs no transfer: it is encoded while the first A piece is still on its way
+            const bool own_b_first = i == 0 && own_b_in_place;
+            if (own_b_first && (rc = scale_b_block(pa, (size_t)g->p))) return rc;
             if ((rc = a_ready(i))) return rc;
             if ((rc = part(pa, GEMMUL8_PART_SCALE_A, r0, r1, 0, 0, "scale A piece"))) return rc;
             ++a_scaled;
@@ -477,11 +497,8 @@ int gemmul8_b200_pgemm(gemmul8_b200_grid *g, gemmul8_b200_pargs *a) {
             const bool per_block = P > 1 && (w % 256) == 0;
             for (size_t d = 0; d < P; ++d) {
                 const size_t pp = ((size_t)g->p + d) % P;
-                if ((rc = b_ready(pp))) return rc;
+                if (!(own_b_first && d == 0) && (rc = scale_b_block(pa, pp))) return rc;
                 const size_t c0 = P > 1 ? pp * w : 0, c1 = P > 1 ? (pp + 1) * w : n_loc;
-                if ((rc = part(pa, GEMMUL8_PART_SCALE_B, 0, 0, c0, c1, "scale B block"))) return rc;
-                ++b_scaled;
-                if ((rc = maybe_ack())) return rc;
                 if (per_block && (rc = part(pa, GEMMUL8_PART_PRODUCT, r0, r1, c0, c1, "product"))) return rc;
             }
             if (!per_block && (rc = part(pa, GEMMUL8_PART_PRODUCT, r0, r1, 0, n_loc, "product"))) return rc;
