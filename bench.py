@@ -463,7 +463,7 @@ def main():
         e2e_ms = e0.elapsed_time(e1) / ksteps
         out["e2e"] = {"value": flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": 8 * (m * k + k * n),
                       "d2h_bytes_per_step": 8 * m * n, "ms_per_step": e2e_ms, "steps": ksteps,
-                      "api": "gemmul8_b200_gemm_host (pinned host A, B, C; 14 x 14 shrinking-block wavefront: H2D, compute and D2H overlap)",
+                      "api": "gemmul8_b200_gemm_host (pinned host A, B, C; block wavefront, 14 row blocks of A x 26 column blocks of B with the last 3/8 of B behind A: H2D, compute and D2H overlap)",
                       "checksum": float(hC[::97, ::89].sum()),
                       "equals_device_resident_result": bool(torch.equal(hC, Cm.cpu()))}
         # the same call with the copies in series (what a caller of the reference does around its gemm)

@@ -973,7 +973,7 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
 
 }  // extern "C"
 
-// Host-buffer call, real types, fast mode, beta == 0: a wavefront over S x S blocks of C (S <= 14, blocks shrinking towards the end).  The H2D
+// Host-buffer call, real types, fast mode, beta == 0: a wavefront over blocks of C (up to 14 row blocks x 26 column blocks).  The H2D
 // stream brings A row blocks and B column blocks alternately (A0, B0, A1, B1, ...); as soon as block
 // pair s is on the device the compute stream scales / encodes it and multiplies everything that has
 // become computable -- the column strip (rows 0..s, column block s) and the row strip (row block s,
@@ -981,10 +981,10 @@ int gemmul8_b200_gemm_blocked(gemmul8_b200_args *a, size_t block_rows, size_t bl
 // are still arriving.  PCIe is full duplex, so the call ends about one strip after the last input
 // byte instead of after (inputs + compute + output) in series.
 // Measured at 16384^3 (PCIe: 55.6 GB/s H2D, 57.2 GB/s D2H alone, ~53 / ~45 GB/s when both run; strided block copies as fast as
-// contiguous ones down to 4 KB runs, tools/pcie_d2h_width.py): 91 - 92 ms.  The last input byte lands at ~81 ms, the last
-// product ends ~5 ms later (2 ms of backlog from the compute-bound end of the wavefront + the last pair's own strips) and the
-// D2H queue drains ~4.5 ms after that (profiles/r02_e2e_timeline.txt).  "All of B, then A in 16 row strips" is slower
-// (105 ms: products can only start once B is complete).
+// contiguous ones down to 4 KB runs in isolation, tools/pcie_d2h_width.py): 85.2 ms with the block schedule below.  With
+// symmetric blocks (A and B ending together) the last input byte lands at ~81 ms, the last product ends ~5 ms later and the
+// D2H queue -- row strips of C -- drains ~4.5 ms after that (profiles/r02_e2e_timeline.txt); "all of B, then A in 16 row
+// strips" is slower still (105 ms: products can only start once B is complete).
 static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     const size_t m = h->m, n = h->n, k = h->k;
     const unsigned N = h->num_moduli, ti = N - 2;
@@ -1008,17 +1008,23 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     const float l2       = oz::host_tab::OZ_LOG2M_FAST[ti];
     const bool split     = oz::host_tab::OZ_M_LO[ti] != 0.0 && h->dtype_C == GEMMUL8_F64;
 
-    // Block boundaries: multiples of 256 rows / columns (whole GEMM tiles), SHRINKING towards the end.  The work a block pair
-    // enables grows with everything that arrived before it, so the call is transfer-bound at first and compute-bound near the
-    // end: what is left when the last input byte has arrived is the backlog plus the last pair's own strips (products and the
-    // D2H of their part of C), proportional to the last block's share.  Timeline measured at 16384^3 (profiles/
-    // r02_e2e_timeline.txt): 12 blocks ending in 1/24 shares 93.0 ms, 14 blocks ending in 1/32 shares 90.9 ms, 18 blocks ending in
-    // 1/64 shares no better (the tail is then the D2H queue, not the last strips).
-    constexpr int kMaxBlocks = 14, kShareSum = 32;
-    static const int weight[kMaxBlocks] = {4, 4, 4, 4, 3, 3, 2, 2, 1, 1, 1, 1, 1, 1};
-    auto bounds = [](size_t len, size_t *b) -> int {
+    // Block boundaries: multiples of 256 rows / columns (whole GEMM tiles), in shares of 1/64 of the dimension.
+    //   steps 0..13  the wavefront proper: A row blocks SHRINKING towards the end, B column blocks in proportion but only up
+    //                to 5/8 of B -- the work a block pair enables grows with everything that arrived before it, so this part
+    //                is transfer-bound and the compute stream keeps up;
+    //   steps 14..25 A is complete: the remaining 3/8 of B arrives in small column blocks, each enabling one full-height
+    //                column strip of C.  Work is now enabled linearly with the bytes that arrive, every strip of C is a
+    //                contiguous D2H (row strips are strided copies with 2-4 KB runs, which reach ~32 GB/s inside this call
+    //                against ~55 GB/s for column strips), and what is left after the last input byte is one 256-column strip.
+    // Measured at 16384^3, one box (profiles/r02_e2e_timeline.txt, r02_ab_e2e_schedule.jsonl): symmetric 12 blocks ending in
+    // 1/24 shares 93.0 ms; symmetric 14 blocks ending in 1/32 shares 90.5 - 90.9; A in 16 blocks with the last 1/4 of B behind
+    // it 86.9; this schedule 85.2.
+    constexpr int kMaxBlocks = 26, kShareSum = 64, kRowBlocks = 14, kColBlocks = 26;
+    static const int row_share[kMaxBlocks] = {8, 8, 8, 8, 6, 6, 4, 4, 2, 2, 2, 2, 2, 2};
+    static const int col_share[kMaxBlocks] = {5, 5, 5, 5, 4, 4, 2, 2, 2, 1, 1, 2, 1, 1, 3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1};
+    auto bounds = [](size_t len, const int *share, int count, size_t *b) -> int {
         const size_t tiles = (len + 255) / 256;
-        if (tiles < (size_t)kShareSum) {        // small problems: equal blocks, at most 8
+        if (tiles < 32) {                       // small problems: equal blocks, at most 8
             const int S = (int)(tiles < 8 ? (tiles ? tiles : 1) : 8);
             for (int i = 0; i <= S; ++i) { size_t x = (tiles * i / S) * 256; b[i] = x < len ? x : len; }
             b[S] = len;
@@ -1026,16 +1032,16 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
         }
         size_t acc = 0;
         b[0] = 0;
-        for (int i = 0; i < kMaxBlocks; ++i) {
-            acc += (size_t)weight[i];
+        for (int i = 0; i < count; ++i) {
+            acc += (size_t)share[i];
             size_t x = (tiles * acc / kShareSum) * 256;
             b[i + 1] = x < len ? x : len;
         }
-        b[kMaxBlocks] = len;
-        return kMaxBlocks;
+        b[count] = len;
+        return count;
     };
     size_t rb[kMaxBlocks + 1], cb[kMaxBlocks + 1];
-    const int SR = bounds(m, rb), SC = bounds(n, cb);
+    const int SR = bounds(m, row_share, kRowBlocks, rb), SC = bounds(n, col_share, kColBlocks, cb);
     const int S = SR > SC ? SR : SC;
 
     struct Res {
@@ -1052,7 +1058,7 @@ static int gemm_host_pipelined(gemmul8_b200_args *h, void *dev_scratch) {
     OZ_CUDA(cudaStreamCreateWithFlags(&r.in, cudaStreamNonBlocking), "stream");
     OZ_CUDA(cudaStreamCreateWithFlags(&r.out, cudaStreamNonBlocking), "stream");
     OZ_CUDA(cudaEventCreateWithFlags(&r.start, cudaEventDisableTiming), "event");
-    for (int i = 0; i < kMaxBlocks; ++i) {
+    for (int i = 0; i < S; ++i) {
         OZ_CUDA(cudaEventCreateWithFlags(&r.evA[i], cudaEventDisableTiming), "event");
         OZ_CUDA(cudaEventCreateWithFlags(&r.evB[i], cudaEventDisableTiming), "event");
         OZ_CUDA(cudaEventCreateWithFlags(&r.evC[2 * i], cudaEventDisableTiming), "event");

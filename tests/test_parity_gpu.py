@@ -553,8 +553,8 @@ def test_host_buffer_entry_equals_device_entry(g):
     (2100, 700, 257, 9, 1, 1, "float64"),        # transposed operands: the strided / contiguous block copies swap
     (777, 777, 640, 6, 0, 1, "float32"),
     (100, 90, 50, 14, 0, 0, "float64"),          # a single block
-    (8292, 8448, 256, 6, 0, 0, "float64"),       # >= 32 tiles per side: the shrinking 14-block schedule, ragged last row block
-    (8192, 2048, 320, 5, 1, 0, "float32"),       # 14 row blocks against 8 equal column blocks
+    (8292, 8448, 256, 6, 0, 0, "float64"),       # >= 32 tiles per side: 14 row x 26 column block schedule, ragged last row block
+    (8192, 2048, 320, 5, 1, 0, "float32"),       # the row-block schedule against 8 equal column blocks
 ])
 def test_host_wavefront_equals_device_entry(g, m, n, k, N, opA, opB, dt):
     """gemm_host's S x S wavefront (block copies overlapped with per-strip scaling, products and CRT)
