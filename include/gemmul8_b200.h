@@ -61,7 +61,7 @@ enum {
                                                Same bits of C; measured slower than the two kernels on B200, see DESIGN.md 3.4 */
     GEMMUL8_FLAG_GEMM_SIMT      = 1u << 8, /* debug: use the CUDA-core int8 GEMM instead of tcgen05   */
     GEMMUL8_FLAG_HOST_SERIAL    = 1u << 9, /* gemm_host: copy in, compute, copy out in series (no wavefront) */
-    GEMMUL8_FLAG_STRIPS         = 1u << 10, /* gemm: column-strip pipeline on three streams (measured slower) */
+    GEMMUL8_FLAG_STRIPS         = 1u << 10, /* gemm: force the column-strip pipeline on three streams (default: by size, option "strips") */
     GEMMUL8_FLAG_ONLY_SCALE_A   = 1u << 11, /* real types: shifts + residues of A only, then return (B may still be in flight) */
     GEMMUL8_FLAG_SKIP_SCALE_A   = 1u << 12, /* real types: A's shifts + residues are already in `work` (previous flag)        */
     GEMMUL8_FLAG_ONLY_BOUND     = 1u << 14, /* real types, accurate mode: bound product only; its int32 row maxima (m) are left at
@@ -127,7 +127,11 @@ int gemmul8_b200_init(int device);
  *   "pair_stages" (OZ_PAIR_STAGES) 0 auto | 4 | 5 | 6     "encode_reference" (GEMMUL8_B200_ENCODE=reference) 0 | 1
  *   "fused_k" (GEMMUL8_B200_FUSED_K) largest k that takes the single-kernel product + CRT path (0 = never)
  *   "scale_fork" (GEMMUL8_B200_SCALE_FORK) 1 | 0: small operands are scaled on two streams side by side
- *   "tma_store" (GEMMUL8_B200_TMA_STORE) 0 | 1: residues of the pair GEMM leave through TMA bulk tensor stores */
+ *   "tma_store" (GEMMUL8_B200_TMA_STORE) 0 | 1: residues of the pair GEMM leave through TMA bulk tensor stores
+ *   "strips" (GEMMUL8_B200_STRIPS) 0 | 1 | 2..8: column-strip pipeline of large real fast-mode calls (encoders of the next
+ *                                  strips of B and the CRT of the previous strip run beside the products): 0 = by size,
+ *                                  1 = never, 2..8 = that many strips whenever the call allows it
+ *   "strip_calls" (read-only)      calls that took that pipeline so far */
 int gemmul8_b200_set_option(const char *name, int value);
 int gemmul8_b200_get_option(const char *name, int *value);
 

@@ -37,7 +37,9 @@ Option g_options[] = {
     {"fused_k", "GEMMUL8_B200_FUSED_K", {0}, 0, 1 << 17},
     {"scale_fork", "GEMMUL8_B200_SCALE_FORK", {1}, 0, 1},
     {"tma_store", "GEMMUL8_B200_TMA_STORE", {0}, 0, 1},
+    {"strips", "GEMMUL8_B200_STRIPS", {0}, 0, 8},
 };
+std::atomic<int> g_strip_calls{0};   // calls that took the column-strip pipeline (read-only option "strip_calls")
 std::once_flag g_options_once;
 void load_options_from_env() {
     std::call_once(g_options_once, [] {
@@ -69,6 +71,7 @@ const Tuning &tuning() {
     t.fused_k          = g_options[5].value.load(std::memory_order_relaxed);
     t.scale_fork       = g_options[6].value.load(std::memory_order_relaxed);
     t.tma_store        = g_options[7].value.load(std::memory_order_relaxed);
+    t.strips           = g_options[8].value.load(std::memory_order_relaxed);
     return t;
 }
 }  // namespace oz
@@ -295,6 +298,15 @@ struct SideStreams {
 };
 thread_local SideStreams g_side;
 
+// Where the pipeline pays (measured on one B200, 14 moduli unless noted; profiles/r02_ab_strips_shapes.jsonl): 16384^3 +3.2 %
+// (20 moduli +8.0 %, 8 moduli +1.3 %), 32768 x 16384 x 16384 +3.4 %, 24576^2 x 8192 +2.2 %, 12288^3 +1.3 %, 16384^2 x 8192 +0.9 %,
+// 8192^2 x 32768 +0.4 %; 16384^2 x 4096 -2.7 %, 8192^3 -4.4 %.  What is hidden grows with k n + m n, what the co-running blocks
+// cost with every strip launch: long k and a large C.
+bool strips_by_size(size_t m, size_t n, size_t k, unsigned N) {
+    (void)N;
+    return k >= 8192 && m >= 8192 && n >= 8192 && m * n >= (size_t)12288 * 12288;
+}
+
 int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
     const size_t m = a->m, n = a->n, k = a->k;
     const unsigned N = a->num_moduli, ti = N - 2;
@@ -317,6 +329,12 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
     for (int i = 0; i <= strips; ++i) { const size_t x = (tiles * i / strips) * 256; cb[i] = x < n ? x : n; }
     cb[strips] = n;
 
+    // phase marks on the caller's stream: start | first product starts | last product ends | end.  Slot 0 is then the EXPOSED
+    // part of the scaling (all of A, and whatever of the first B strip is not ready by then), slot 1 the products back to back,
+    // slot 3 the exposed CRT of the last strip; the rest of the scaling and of the CRT runs beside the products.
+    PhaseTimer timer(a->flags, st);
+    timer.mark();
+    oz::g_strip_calls.fetch_add(1, std::memory_order_relaxed);
     OZ_CUDA(cudaEventRecord(S.start, st), "event record");
     OZ_CUDA(cudaStreamWaitEvent(S.sB, S.start, 0), "stream wait");
     for (int j = 0; j < strips; ++j) {
@@ -339,6 +357,7 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
     for (int j = 0; j < strips; ++j) {
         const size_t c0 = cb[j], c1 = cb[j + 1];
         OZ_CUDA(cudaStreamWaitEvent(st, S.evB[j], 0), "stream wait");
+        if (j == 0) timer.mark();
         if (c1 <= c0) continue;
         gp.B8i = B8i + c0 * L.lda8i; gp.rowsB = c1 - c0; gp.C8u = C8u + c0 * L.m_pad;
         OZ_CUDA(oz::launch_gemm_tcgen05(gp, oz::EPI_RESIDUE, st), "int8 gemm");
@@ -347,8 +366,11 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
         OZ_CUDA(oz::launch_crt(a->dtype_C, split, N, m, c1 - c0, gp.C8u, L.m_pad, L.sizeC, static_cast<uint8_t *>(a->C) + c0 * a->ldc * esC,
                                a->ldc, sftA, sftB + c0, a->alpha, a->beta, dev_scalars(a), S.sC), "crt");
     }
+    timer.mark();
     OZ_CUDA(cudaEventRecord(S.done, S.sC), "event record");
     OZ_CUDA(cudaStreamWaitEvent(st, S.done, 0), "stream wait");
+    timer.mark();
+    timer.finish(a->timers_ns);
     return GEMMUL8_OK;
 }
 
@@ -371,13 +393,19 @@ int gemm_real(gemmul8_b200_args *a) {
     const bool simt      = (a->flags & GEMMUL8_FLAG_GEMM_SIMT) != 0;
     auto gemm = simt ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
 
-    // opt-in (GEMMUL8_FLAG_STRIPS): the column-strip pipeline above.  Measured SLOWER than the phases in series on
-    // B200 (56.0 vs 51.2 ms at 16384^3, profiles/r01_gemm_schedule_variants.log): blocks of the side streams
-    // delay CTAs of the statically scheduled persistent GEMM, which costs more than the overlap saves.
+    // The column-strip pipeline above, for large plain fast-mode calls.  With the round-1 kernel it was slower than the phases
+    // in series (56.0 vs 51.2 ms at 16384^3); with the pair kernel, whose 4-stage form leaves room on every SM, it wins where
+    // the hidden scaling + CRT outweigh what the co-running blocks cost the statically scheduled products
+    // (profiles/r02_ab_strips.jsonl: 16384^3 48.97 -> 47.45 ms; 8192^3 5.42 -> 5.67 ms, i.e. not there).
+    // Option "strips": 0 = by size (strips_by_size), 1 = never, 2 ... 8 = that many strips; GEMMUL8_FLAG_STRIPS forces it.
     const unsigned serial_flags = GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_STAGE_SCALING | GEMMUL8_FLAG_STAGE_RESIDUES | GEMMUL8_FLAG_FUSED_CRT |
-                                  GEMMUL8_FLAG_GEMM_SIMT;
-    if ((a->flags & GEMMUL8_FLAG_STRIPS) && a->fastmode && !(a->flags & serial_flags) && n >= 2048 && g_side.init()) {
-        const int strips = n >= 8192 ? 4 : 2;
+                                  GEMMUL8_FLAG_GEMM_SIMT | GEMMUL8_FLAG_SKIP_SCALE_A | GEMMUL8_FLAG_ONLY_SCALE_A | GEMMUL8_FLAG_ONLY_BOUND |
+                                  GEMMUL8_FLAG_SKIP_BOUND;
+    const int strips_opt = oz::tuning().strips;
+    const bool strips_wanted = (a->flags & GEMMUL8_FLAG_STRIPS) || strips_opt >= 2 || (strips_opt == 0 && strips_by_size(m, n, k, N));
+    if (strips_wanted && a->fastmode && !(a->flags & serial_flags) && !take_fused(a) && n >= 2048 && oz::tuning().gemm_pair != 0 &&
+        g_side.init()) {
+        const int strips = strips_opt >= 2 ? (strips_opt < (int)((n + 255) / 256) ? strips_opt : (int)((n + 255) / 256)) : (n >= 8192 ? 4 : 2);
         return gemm_real_strips(a, L, strips);
     }
 
@@ -1228,6 +1256,10 @@ int gemmul8_b200_set_option(const char *name, int value) {
 
 int gemmul8_b200_get_option(const char *name, int *value) {
     oz::load_options_from_env();
+    if (name && value && !strcmp(name, "strip_calls")) {   // read-only counter: calls that took the column-strip pipeline
+        *value = oz::g_strip_calls.load(std::memory_order_relaxed);
+        return GEMMUL8_OK;
+    }
     oz::Option *o = oz::find_option(name);
     if (!o || !value) return fail(GEMMUL8_ERR_ARGUMENT, "get_option: unknown option");
     *value = o->value.load(std::memory_order_relaxed);

@@ -163,6 +163,11 @@ def test_options_api_without_a_device(g):
     g.set_option("pair_band", 4)
     assert g.get_option("pair_band") == 4
     g.set_option("pair_band", old)
+    assert g.get_option("strips") == 0 and g.get_option("strip_calls") == 0     # pipeline by size; nothing has run here
+    with pytest.raises(Exception):
+        g.set_option("strip_calls", 1)                                           # a read-only counter
+    with pytest.raises(Exception):
+        g.set_option("strips", 9)
     with pytest.raises(g.Gemmul8Error):
         g.set_option("no_such_option", 1)
     with pytest.raises(g.Gemmul8Error):

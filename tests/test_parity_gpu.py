@@ -483,13 +483,31 @@ def test_phase_log_records_without_synchronising(g):
 
 
 def test_strip_pipeline_equals_default(g):
-    """The opt-in three-stream column-strip schedule (FLAG_STRIPS) against the default: bit-identical."""
+    """The three-stream column-strip schedule (taken by size for large calls; forced here by FLAG_STRIPS and by the option
+    "strips") against the phases in series: bit-identical, counted, and its phase log has the three spans."""
     torch = torch_()
     m, n, k, N = 1500, 4500, 700, 14
     A, B = operands(g, m, n, k, 0, 1, torch.float64, torch.float64, seedB=12)
+    calls0 = g.get_option("strip_calls")
     C, v = run_ours(g, m, n, k, N, True, A, B, 0, 1)
+    assert g.get_option("strip_calls") == calls0          # small call: phases in series
     Cs, vs = run_ours(g, m, n, k, N, True, A, B, 0, 1, flags=g.FLAG_STRIPS)
+    assert g.get_option("strip_calls") == calls0 + 1
     assert torch.equal(v["C8u"][:, :, :m], vs["C8u"][:, :, :m]) and torch.equal(C, Cs)
+    g.set_option("strips", 3)
+    try:
+        g.phase_log_collect()
+        C3, v3 = run_ours(g, m, n, k, N, True, A, B, 0, 1, flags=g.FLAG_PHASE_LOG)
+        torch.cuda.synchronize()
+        ph, calls = g.phase_log_collect()
+        assert g.get_option("strip_calls") == calls0 + 2 and calls == 1
+        assert ph[0] > 0 and ph[1] > 0 and ph[3] > 0
+        assert torch.equal(v["C8u"][:, :, :m], v3["C8u"][:, :, :m]) and torch.equal(C, C3)
+        g.set_option("strips", 1)                          # never, whatever the size
+        C1, _ = run_ours(g, m, n, k, N, True, A, B, 0, 1)
+        assert g.get_option("strip_calls") == calls0 + 2 and torch.equal(C, C1)
+    finally:
+        g.set_option("strips", 0)
 
 
 def test_leading_dimensions_and_determinism(g):
@@ -594,8 +612,16 @@ def test_benchmark_size_properties(g):
         assert torch.equal(got, want), j
     checksum = C.sum().item()
     del v
+    calls0 = g.get_option("strip_calls")
     C4, _ = run_ours(g, m, n, k, N, True, A, B, alpha=4.0)
     assert torch.equal(C4, 4.0 * C) and np.isfinite(checksum)
+    assert g.get_option("strip_calls") == calls0 + 1      # this size takes the column-strip pipeline by default ...
+    g.set_option("strips", 1)
+    try:                                                   # ... and the phases in series give the same bits
+        C4, _ = run_ours(g, m, n, k, N, True, A, B, alpha=4.0)
+    finally:
+        g.set_option("strips", 0)
+    assert torch.equal(C4, 4.0 * C) and g.get_option("strip_calls") == calls0 + 1
     del C4
     ri = rows.to(torch.int32)[:32].sort().values.contiguous()
     ci = cols.to(torch.int32)[:32].sort().values.contiguous()
