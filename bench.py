@@ -121,14 +121,16 @@ def peaks():
     return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(m_loc, n_loc, k, N):
+def ncu_traffic(m_loc, n_loc, k, N, strips=False):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the most recent committed
     `ncu --set full` capture of this shape (profiles/r*_ncu_traffic.json, written by tools/ncu_traffic.py; a run cannot
-    read DRAM counters itself); null for other per-GPU shapes.  Returns (bytes, file)."""
+    read DRAM counters itself); null for other per-GPU shapes.  `strips`: the call went through the column-strip pipeline, whose
+    product launches are quarter problems (profiles/r*_ncu_traffic_strips.json).  Returns (bytes, file)."""
     if (m_loc, n_loc, k, N) != (16384, 16384, 16384, 14):
         return None, None
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+    pattern = "r*_ncu_traffic_strips.json" if strips else "r*_ncu_traffic.json"
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)), reverse=True):
         try:
             return json.load(open(path))[dominant_kernel()]["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
         except Exception:
@@ -496,7 +498,7 @@ def main():
         peak = bf16x2
         peak_source = f"2 x bf16 {kind} of {peak_src} (no int8 cuBLASLt path in this torch: {i8['error']})"
     ach = per_gpu_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic, traffic_file = ncu_traffic(m_loc, n_loc, k, N)
+    traffic, traffic_file = ncu_traffic(m_loc, n_loc, k, N, strips_used)
     out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                        "traffic": traffic, "traffic_source": traffic_file,
                        "kernel": dominant_kernel() + " (all moduli in one launch, residue reduction in the epilogue)", "kernel_ms": gemm_ms,

@@ -270,8 +270,10 @@ int block_to_c(const gemmul8_b200_args *a, oz::GemmProblem &gp, bool fused, bool
 //     side stream B : shifts + residues of B columns [strip j+1]
 //     caller stream : shifts + residues of all of A, then the all-moduli product of strip j
 //     side stream C : CRT of strip j-1
-// run concurrently (the persistent GEMM CTAs use 48 registers per thread and leave room on every SM
-// for the encode / CRT blocks).  Streams and events are created once per host thread and device.
+// run concurrently: a pair CTA of the product owns its SM, so the overlap is between SMs -- where one strip's CTAs have
+// finished, the next strip's encoders and the previous strip's CRT run until the next product's CTAs arrive -- and in the
+// power budget (the HBM-bound phases no longer run with the tensor pipe idle).  Streams and events are created once per
+// host thread and device.
 // ---------------------------------------------------------------------------------------------
 struct SideStreams {
     int device = -1;
@@ -353,7 +355,9 @@ int gemm_real_strips(gemmul8_b200_args *a, const oz::Layout &L, int strips) {
     oz::GemmProblem gp{};
     gp.A8i = A8i; gp.rowsA = m; gp.ld8i = L.lda8i; gp.sizeA = L.sizeA; gp.sizeB = L.sizeB; gp.num_slices = N; gp.first_modulus = 0;
     gp.ldc8u = L.m_pad; gp.sizeC = L.sizeC; gp.claims = claims_of(work, L);
-    gp.share_sm = true;   // encoder / CRT blocks of the side streams must fit beside the persistent GEMM CTAs
+    // Full pipeline depth (6 stages): at 95 registers x 640 threads a pair CTA owns its SM anyway, the side streams' blocks run
+    // on SMs between two strip launches' CTAs, not beside them; the 4-stage form only lost tensor-pipe time
+    // (profiles/r02_ab_strips_stages.jsonl: 16384^3 47.3 -> 45.7 ms, 12288^3 20.6 -> 19.6 ms).
     for (int j = 0; j < strips; ++j) {
         const size_t c0 = cb[j], c1 = cb[j + 1];
         OZ_CUDA(cudaStreamWaitEvent(st, S.evB[j], 0), "stream wait");
