@@ -398,7 +398,7 @@ int gemm_real(gemmul8_b200_args *a) {
     auto gemm = simt ? oz::launch_gemm_simt : oz::launch_gemm_tcgen05;
 
     // The column-strip pipeline above, for large plain fast-mode calls.  With the round-1 kernel it was slower than the phases
-    // in series (56.0 vs 51.2 ms at 16384^3); with the pair kernel, whose 4-stage form leaves room on every SM, it wins where
+    // in series (56.0 vs 51.2 ms at 16384^3); with the pair kernel it wins where
     // the hidden scaling + CRT outweigh what the co-running blocks cost the statically scheduled products
     // (profiles/r02_ab_strips.jsonl: 16384^3 48.97 -> 47.45 ms; 8192^3 5.42 -> 5.67 ms, i.e. not there).
     // Option "strips": 0 = by size (strips_by_size), 1 = never, 2 ... 8 = that many strips; GEMMUL8_FLAG_STRIPS forces it.
