@@ -402,7 +402,9 @@ int gemm_real(gemmul8_b200_args *a) {
     // the hidden scaling + CRT outweigh what the co-running blocks cost the statically scheduled products
     // (profiles/r02_ab_strips.jsonl: 16384^3 48.97 -> 47.45 ms; 8192^3 5.42 -> 5.67 ms, i.e. not there).
     // Option "strips": 0 = by size (strips_by_size), 1 = never, 2 ... 8 = that many strips; GEMMUL8_FLAG_STRIPS forces it.
-    const unsigned serial_flags = GEMMUL8_FLAG_TIMERS | GEMMUL8_FLAG_STAGE_SCALING | GEMMUL8_FLAG_STAGE_RESIDUES | GEMMUL8_FLAG_FUSED_CRT |
+    // (GEMMUL8_FLAG_TIMERS does not exclude it: the synchronous drop-in call takes the pipeline too, and its four numbers are
+    // then the exposed scaling, the products back to back, 0, and the exposed CRT)
+    const unsigned serial_flags = GEMMUL8_FLAG_STAGE_SCALING | GEMMUL8_FLAG_STAGE_RESIDUES | GEMMUL8_FLAG_FUSED_CRT |
                                   GEMMUL8_FLAG_GEMM_SIMT | GEMMUL8_FLAG_SKIP_SCALE_A | GEMMUL8_FLAG_ONLY_SCALE_A | GEMMUL8_FLAG_ONLY_BOUND |
                                   GEMMUL8_FLAG_SKIP_BOUND;
     const int strips_opt = oz::tuning().strips;
